@@ -1,0 +1,175 @@
+/*
+ * lsk.h — C ABI of the B200-native LayerSkip self-speculative decoding engine (liblsk.so).
+ *
+ * The reference (facebookresearch/LayerSkip) has NO FFI: its hot path is Python calling
+ * HuggingFace modules.  This ABI is what a binding for that path would bind; each entry point
+ * names the reference code it replaces (paths relative to the reference root).  Plain C types
+ * only — device pointers travel as `const void*`, streams are owned by the engine.  Every call
+ * returns 0 on success or a negative lsk_status; the text is available from lsk_last_error().
+ * Not re-entrant: one host thread drives one engine (the reference is single-threaded too,
+ * self_speculation/generator_base.py:97-130).
+ */
+#ifndef LSK_H_
+#define LSK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSK_ABI_VERSION 1
+#define LSK_MAX_SPEC 15      /* D_max: verify handles up to 16 rows (D+1)                    */
+#define LSK_MAX_EOS 8
+
+typedef enum {
+  LSK_OK = 0,
+  LSK_ERR_INVALID = -1,      /* bad argument / unsupported shape                             */
+  LSK_ERR_CUDA = -2,         /* CUDA runtime error (message has the CUDA string)             */
+  LSK_ERR_STATE = -3,        /* call order violated (e.g. round before prefill)              */
+  LSK_ERR_NCCL = -4,
+  LSK_ERR_NOMEM = -5,
+  LSK_ERR_CTX = -6           /* sequence would exceed max_ctx                                */
+} lsk_status;
+
+/* flags */
+#define LSK_FLAG_KEEP_LOGITS 1u  /* also store fp32 logits (needed for sampling / debug reads) */
+#define LSK_FLAG_NO_PDL 2u       /* disable programmatic dependent launch                    */
+#define LSK_FLAG_NO_GRAPH 4u     /* launch kernels eagerly instead of replaying CUDA graphs  */
+
+/* Llama architecture + engine sizing.  Replaces what the reference reads off the HF model
+ * object (`model.config`, generate.py:54-67). */
+typedef struct {
+  int32_t vocab, hidden, inter, n_layers, n_heads, n_kv_heads, head_dim;
+  float rms_eps, rope_theta;
+  int32_t max_ctx;           /* prompt + generated tokens the KV pool must hold              */
+  int32_t tp_rank, tp_size;  /* tensor-parallel shard of this process (1 process per GPU)    */
+  int32_t attn_splits;       /* split-KV factor (0 = default)                                */
+  uint32_t flags;
+} lsk_config;
+
+/* Which HF tensor a weight descriptor carries (names as in
+ * transformers LlamaForCausalLM.state_dict(); call sites llama_model_utils.py:182,193,204-205). */
+typedef enum {
+  LSK_W_EMBED = 0,           /* model.embed_tokens.weight            [vocab, hidden]          */
+  LSK_W_FINAL_NORM = 1,      /* model.norm.weight                    [hidden]                 */
+  LSK_W_LM_HEAD = 2,         /* lm_head.weight                       [vocab, hidden]          */
+  LSK_W_LN1 = 3,             /* layers.i.input_layernorm.weight      [hidden]                 */
+  LSK_W_Q = 4, LSK_W_K = 5, LSK_W_V = 6, LSK_W_O = 7,   /* self_attn.{q,k,v,o}_proj.weight     */
+  LSK_W_LN2 = 8,             /* layers.i.post_attention_layernorm.weight                      */
+  LSK_W_GATE = 9, LSK_W_UP = 10, LSK_W_DOWN = 11         /* mlp.{gate,up,down}_proj.weight      */
+} lsk_weight_role;
+
+/* One full (unsharded) bf16 tensor in DEVICE memory, row-major [rows, cols] as HF stores it.
+ * The engine slices its tensor-parallel shard, repacks it into its own HBM layout and does not
+ * keep the pointer: the caller may free the tensor when lsk_load_weights returns. */
+typedef struct {
+  int32_t role;              /* lsk_weight_role                                              */
+  int32_t layer;             /* decoder layer index, ignored for embed / final norm / head   */
+  const void* data;          /* device pointer, bf16                                         */
+  int64_t rows, cols;
+} lsk_weight_desc;
+
+/* Per-generation settings: `GenerationConfig` (self_speculation/generator_base.py:33-49) plus the
+ * eos list built at generator_base.py:106. */
+typedef struct {
+  int32_t exit_layer;        /* E; <= 0 means "all layers" for lsk_ar_step                   */
+  int32_t max_steps;
+  int32_t n_eos;
+  int32_t eos_ids[LSK_MAX_EOS];
+  int32_t sample;            /* 0 greedy (arg-max), 1 sampling                               */
+  float temperature;
+  int32_t top_k;
+  float top_p;
+  uint64_t seed;             /* counter-based RNG seed for the sampling path                 */
+} lsk_generation;
+
+/* What one speculation round produced — everything
+ * SelfSpeculativeGenerationStrategy.single_step_speculation returns or streams
+ * (self_speculation_generator.py:102-229): the draft ids (for SpeculativeTextStreamer, :158-161),
+ * number_of_matches (:185-199), the tokens appended to output_ids (:203-205). */
+typedef struct {
+  int32_t n_drafted;                     /* D_actual (EOS can end the draft loop early)       */
+  int32_t n_matches;
+  int32_t n_emitted;                     /* n_matches + 1                                     */
+  int32_t kv_len;                        /* committed context after the round                 */
+  int32_t draft_ids[LSK_MAX_SPEC + 1];
+  int32_t emitted_ids[LSK_MAX_SPEC + 1]; /* draft[:n] + [verified[n]]                         */
+  int32_t verified_ids[LSK_MAX_SPEC + 1];
+} lsk_round_out;
+
+typedef struct lsk_engine lsk_engine;
+
+int lsk_abi_version(void);
+const char* lsk_last_error(void);
+
+/* Engine lifetime.  Allocates packed-weight storage, the paged KV pool, scratch and streams on
+ * the CURRENT CUDA device.  Replaces model placement in generate.py:54-67. */
+int lsk_create(const lsk_config* cfg, lsk_engine** out);
+void lsk_destroy(lsk_engine* e);
+
+/* Tensor-parallel wiring (configs with tp_size > 1): rank 0 calls lsk_comm_unique_id, the host
+ * side broadcasts the 128 bytes, every rank calls lsk_comm_init.  The reference has no
+ * equivalent (generate.py:50-52 exits on non-zero ranks). */
+int lsk_comm_unique_id(uint8_t id_out[128]);
+int lsk_comm_init(lsk_engine* e, const uint8_t id[128]);
+
+/* Weight ingest: HF tensors -> packed / sharded HBM layout.  Synchronous. */
+int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n);
+/* 1 when every tensor the architecture needs has been loaded. */
+int lsk_weights_complete(const lsk_engine* e);
+
+/* Start a generation: reset lengths, store E / eos / sampling.  Replaces the state reset at
+ * self_speculation_generator.py:41-50. */
+int lsk_begin(lsk_engine* e, const lsk_generation* gen);
+
+/* Prompt ingestion from HOST memory (ids[n], n >= 1).  Runs ids[0..n-2] through all layers (the
+ * work the reference does inside its first forward_early + forward_remainder,
+ * llama_model_utils.py:251-261, 363-383) so that afterwards every round has the steady-state
+ * shape: one pending input token (ids[n-1]) and kv_len == n-1 in every layer. */
+int lsk_prefill(lsk_engine* e, const int32_t* ids, int32_t n);
+
+/* One draft / verify / accept / commit round with d_req speculations
+ * (self_speculation_generator.py:102-229; the caller applies the max_steps clamp of :63-66).
+ * d_req == 0 is the reference's tail round.  Blocks until the round's result is on the host. */
+int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out);
+
+/* One autoregressive step on the same engine (autoregressive_generator.py:44-67): all layers, or
+ * layers < E when the generation's exit_layer > 0.  Returns the chosen token; the caller decides
+ * about EOS exactly as the reference does (:66-67). */
+int lsk_ar_step(lsk_engine* e, int32_t* token_out);
+
+/* Queries / debugging (parity tests). */
+int lsk_kv_len(const lsk_engine* e, int32_t* len_out);
+typedef enum {
+  LSK_DBG_HIDDEN = 0,        /* fp32 [16, hidden] residual-stream rows of the last launch     */
+  LSK_DBG_LOGITS = 1,        /* fp32 [16, vocab_local] (needs LSK_FLAG_KEEP_LOGITS)           */
+  LSK_DBG_KROW = 2,          /* bf16->fp32 K cache row: layer, index = kv_head*max_ctx + pos  */
+  LSK_DBG_VROW = 3
+} lsk_debug_what;
+int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index,
+                   float* dst_host, int64_t n_floats);
+/* Replace the (identity) logical->physical KV page map with a permutation: proves the paged
+ * indirection.  Only valid before lsk_prefill. */
+int lsk_debug_set_page_table(lsk_engine* e, const int32_t* pages, int32_t n_pages);
+
+/* Bytes of HBM the engine streams for one (d, ctx) round / AR step — the algorithmic-bytes
+ * model of SURVEY.md §8(d), per GPU (tensor-parallel shards included). */
+int lsk_round_bytes(const lsk_engine* e, int32_t d, int32_t ctx, double* bytes_out);
+int lsk_ar_bytes(const lsk_engine* e, int32_t ctx, double* bytes_out);
+/* Kernels launched (or replayed through graphs) since lsk_create; device time of the last
+ * lsk_round / lsk_ar_step / lsk_prefill measured with CUDA events on the engine's stream. */
+int lsk_launch_count(const lsk_engine* e, int64_t* count_out);
+int lsk_last_device_ms(const lsk_engine* e, float* ms_out);
+
+/* Stand-alone kernel entry points used by the micro-benchmarks and unit tests: run the skinny
+ * GEMM (y[m, n] = x[m, k] . W[n, k]^T, fp32 out) on packed weights / the split-KV attention on
+ * caller-provided device buffers. */
+int lsk_test_pack(const void* w_bf16_dev, int64_t n, int64_t k, void* packed_out_dev);
+int lsk_test_gemm(const void* packed_dev, int64_t n, int64_t k, const void* x_bf16_dev,
+                  int32_t m, float* y_dev, int32_t iters, float* avg_ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSK_H_ */

@@ -1,0 +1,895 @@
+// engine.cu — liblsk: C ABI (include/lsk.h) + host-side orchestration of the sm_100a kernels.
+//
+// The engine owns: packed weights, the paged KV pool, scratch activations, the device-resident
+// generation state, one stream and a cache of CUDA graphs (one per (E, d_req) round shape).
+// A speculation round is ONE graph replay and ONE host synchronisation.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lsk.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_skinny.cuh"
+#include "misc_kernels.cuh"
+
+using namespace lsk;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(LSK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define NC(expr)                                                                         \
+  do {                                                                                   \
+    ncclResult_t _r = (expr);                                                            \
+    if (_r != ncclSuccess)                                                               \
+      return fail(LSK_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(_r),  \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int _s = (expr);         \
+    if (_s != LSK_OK) return _s; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------
+struct LayerWeights {
+  __nv_bfloat16* wqkv = nullptr;  // packed [(q_rows + 2 kv_rows), hidden]
+  __nv_bfloat16* wo = nullptr;    // packed [hidden, q_rows]
+  __nv_bfloat16* wgu = nullptr;   // packed [2 * inter_l, hidden]  (gate/up interleaved by 8)
+  __nv_bfloat16* wd = nullptr;    // packed [hidden, inter_l]
+  __nv_bfloat16* ln1 = nullptr;
+  __nv_bfloat16* ln2 = nullptr;
+  unsigned loaded = 0;            // bit per role
+};
+
+struct GemmPlan {
+  int n_tiles = 0, nsb = 0, K = 0, ks_log2 = 0, grid = 0;
+};
+
+struct lsk_engine {
+  lsk_config cfg{};
+  int sm_count = 0;
+  // local (tensor-parallel shard) dimensions
+  int heads_l = 0, kv_heads_l = 0, q_rows = 0, kv_rows = 0, inter_l = 0, vocab_l = 0,
+      vocab_l_pad = 0, vocab_off = 0, group = 0;
+  int n_pages = 0, max_pos = 0, n_splits = 0;
+  bool use_pdl = true, use_graph = true, keep_logits = false;
+
+  std::vector<LayerWeights> layers;
+  __nv_bfloat16* embed = nullptr;      // [vocab, hidden] natural (replicated)
+  __nv_bfloat16* final_norm = nullptr;
+  __nv_bfloat16* lm_head = nullptr;    // packed [vocab_l_pad, hidden]
+  unsigned globals_loaded = 0;
+
+  __nv_bfloat16* kpool = nullptr;      // [layer][page][kv_head][64][128]
+  __nv_bfloat16* vpool = nullptr;
+  size_t pool_layer_elems = 0;
+  int* page_table = nullptr;
+  float2* rope = nullptr;
+
+  float* hidden = nullptr;             // [16][hidden] fp32 residual-stream rows
+  __nv_bfloat16* qbuf = nullptr;       // [16][q_rows]
+  __nv_bfloat16* attn_out = nullptr;   // [16][q_rows]
+  __nv_bfloat16* act = nullptr;        // [16][inter_l]
+  float* tp_buf = nullptr;             // [16][hidden] row-parallel partial sums (TP)
+  float* logits = nullptr;             // [16][vocab_l_pad] (optional)
+  float* cand_val = nullptr;           // [n_cand_max][16]
+  int* cand_idx = nullptr;
+  float* gath_val = nullptr;           // TP: [tp_size][16]
+  int* gath_idx = nullptr;
+  float* rank_val = nullptr;           // TP: [16]
+  int* rank_idx = nullptr;
+  float* part_o = nullptr;
+  float* part_ml = nullptr;
+  int* tickets = nullptr;
+  int* d_zero = nullptr;
+  int* d_prompt = nullptr;             // [max_ctx] prompt ids
+  DevState* state = nullptr;
+  GenParams* gen_dev = nullptr;
+  RoundResult* res_host = nullptr;     // mapped pinned
+  RoundResult* res_dev = nullptr;      // device alias of res_host
+
+  GemmPlan p_qkv, p_o, p_gu, p_d, p_lm;
+  int lm_cand = 0;                     // candidates produced by the LM head (its grid)
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<long long, cudaGraphExec_t> graphs;
+  ncclComm_t comm = nullptr;
+
+  lsk_generation gen{};
+  bool began = false, prefilled = false;
+  int host_len = 0;                    // host mirror of the committed KV length
+  int seq = 0;
+  int64_t launches = 0;
+  int64_t capture_launches = 0;        // launches recorded while capturing the current graph
+  std::map<long long, int64_t> graph_launches;
+  float last_ms = 0.f;
+};
+
+static constexpr int kSmemMax = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------------
+// launch helper (programmatic dependent launch attribute on every kernel)
+// ---------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(lsk_engine* e, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                          size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = e->use_pdl ? 1 : 0;
+  e->launches += 1;
+  e->capture_launches += 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM planning / dispatch
+// ---------------------------------------------------------------------------------------------
+static GemmPlan make_plan(int n_rows, int K, int sm_count) {
+  GemmPlan p;
+  p.n_tiles = n_rows / 16;
+  p.K = K;
+  p.nsb = K / 32;
+  // K-split across the 16 warps of a CTA: largest power of two that divides nsb and leaves each
+  // warp >= 8 super-blocks (one full prefetch window) to stream.
+  int ks_log2 = 0;
+  while (ks_log2 < 4 && (p.nsb % (2 << ks_log2)) == 0 && p.nsb / (2 << ks_log2) >= 8) ++ks_log2;
+  if (const char* env = getenv("LSK_FORCE_KS_LOG2")) {
+    int f = atoi(env);
+    if (f >= 0 && f <= 4 && p.nsb % (1 << f) == 0) ks_log2 = f;
+  }
+  p.ks_log2 = ks_log2;
+  const int tpc = kGemmWarps >> ks_log2;
+  const int n_groups = (p.n_tiles + tpc - 1) / tpc;
+  // persistent grid: the CTA count <= SMs that wastes the fewest group slots (HBM-bound, so an
+  // exact divisor on fewer SMs beats a ragged last wave on all of them); ties -> more CTAs.
+  int best_g = 1;
+  long best_cost = -1;
+  const int lo = sm_count / 2 > 0 ? sm_count / 2 : 1;
+  for (int g = lo; g <= sm_count; ++g) {
+    const long cost = (long)((n_groups + g - 1) / g) * g;
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && g > best_g)) {
+      best_cost = cost;
+      best_g = g;
+    }
+  }
+  p.grid = n_groups < lo ? n_groups : best_g;
+  if (p.grid > n_groups) p.grid = n_groups;
+  return p;
+}
+
+template <int NT, int PRO, int EPI>
+static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
+  static bool configured = false;
+  auto kern = gemm_skinny_kernel<NT, PRO, EPI>;
+  if (!configured) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured = true;
+  }
+  const size_t smem = gemm_smem_bytes<NT>(p.K, EPI, p.ks_log2);
+  if (smem > (size_t)kSmemMax)
+    return fail(LSK_ERR_INVALID, "skinny GEMM needs %zu B shared memory (K=%d, NT=%d)", smem, p.K, NT);
+  a.n_tiles = p.n_tiles;
+  a.nsb = p.nsb;
+  a.K = p.K;
+  a.ks_log2 = p.ks_log2;
+  CU(launch(e, kern, dim3(p.grid), dim3(kGemmThreads), smem, a));
+  return LSK_OK;
+}
+
+template <int PRO, int EPI>
+static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
+  if (a.M <= 8) return launch_gemm_t<1, PRO, EPI>(e, p, a);
+  if (gemm_smem_bytes<2>(p.K, EPI, p.ks_log2) <= (size_t)kSmemMax)
+    return launch_gemm_t<2, PRO, EPI>(e, p, a);
+  // 16 rows do not fit next to this K: two 8-row passes (only RESID/STORE shapes get here)
+  GemmArgs lo = a, hi = a;
+  lo.M = 8;
+  hi.M = a.M - 8;
+  hi.x_bf16 = a.x_bf16 ? a.x_bf16 + (size_t)8 * a.xb_ld : nullptr;
+  hi.x_f32 = a.x_f32 ? a.x_f32 + (size_t)8 * a.x_ld : nullptr;
+  hi.out_f32 = a.out_f32 ? a.out_f32 + (size_t)8 * a.out_ld : nullptr;
+  if (EPI != EPI_RESID && EPI != EPI_STORE)
+    return fail(LSK_ERR_INVALID, "row-split fallback only supports RESID/STORE epilogues");
+  TRY((launch_gemm_t<1, PRO, EPI>(e, p, lo)));
+  return launch_gemm_t<1, PRO, EPI>(e, p, hi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one decoder layer on hidden rows [row0, row0 + M) at positions *base_len + pos_off + i
+//   (HF LlamaDecoderLayer as called at llama_model_utils.py:193-201,253-261,354-362,375-383)
+// ---------------------------------------------------------------------------------------------
+static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base_len, int pos_off) {
+  const lsk_config& c = e->cfg;
+  LayerWeights& L = e->layers[li];
+  float* x = e->hidden + (size_t)row0 * c.hidden;
+  __nv_bfloat16* kp = e->kpool + (size_t)li * e->pool_layer_elems;
+  __nv_bfloat16* vp = e->vpool + (size_t)li * e->pool_layer_elems;
+  const bool tp = c.tp_size > 1;
+
+  {  // RMSNorm -> QKV -> RoPE -> KV append
+    GemmArgs a{};
+    a.W = reinterpret_cast<const uint4*>(L.wqkv);
+    a.M = M;
+    a.x_f32 = x; a.x_ld = c.hidden; a.norm_w = L.ln1; a.eps = c.rms_eps;
+    a.q_out = e->qbuf; a.q_ld = e->q_rows;
+    a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
+    a.base_len = base_len; a.pos_off = pos_off; a.rope = e->rope;
+    a.q_rows = e->q_rows; a.kv_rows = e->kv_rows; a.n_kv_heads = e->kv_heads_l;
+    TRY((launch_gemm<PRO_RMS, EPI_QKV>(e, e->p_qkv, a)));
+  }
+  {  // attention over the paged cache
+    AttnArgs a{};
+    a.q = e->qbuf; a.q_ld = e->q_rows; a.out = e->attn_out; a.out_ld = e->q_rows;
+    a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
+    a.base_len = base_len; a.pos_off = pos_off; a.M = M; a.group = e->group;
+    a.n_kv_heads = e->kv_heads_l; a.n_splits = e->n_splits;
+    a.scale = 1.0f / sqrtf((float)c.head_dim);
+    a.part_o = e->part_o; a.part_ml = e->part_ml; a.rows_pad = e->group * 16;
+    a.tickets = e->tickets;
+    CU(launch(e, attn_splitkv_kernel, dim3(e->kv_heads_l, e->n_splits), dim3(kAttnThreads), 0, a));
+  }
+  {  // O projection (+ residual, or all-reduce then residual under TP)
+    GemmArgs a{};
+    a.W = reinterpret_cast<const uint4*>(L.wo);
+    a.M = M;
+    a.x_bf16 = e->attn_out; a.xb_ld = e->q_rows;
+    if (!tp) {
+      a.out_f32 = x; a.out_ld = c.hidden;
+      TRY((launch_gemm<PRO_BF16, EPI_RESID>(e, e->p_o, a)));
+    } else {
+      a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
+      TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_o, a)));
+      NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+      CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
+    }
+  }
+  {  // RMSNorm -> gate/up -> SiLU * up
+    GemmArgs a{};
+    a.W = reinterpret_cast<const uint4*>(L.wgu);
+    a.M = M;
+    a.x_f32 = x; a.x_ld = c.hidden; a.norm_w = L.ln2; a.eps = c.rms_eps;
+    a.act = e->act; a.act_ld = e->inter_l;
+    TRY((launch_gemm<PRO_RMS, EPI_SILU>(e, e->p_gu, a)));
+  }
+  {  // down projection (+ residual)
+    GemmArgs a{};
+    a.W = reinterpret_cast<const uint4*>(L.wd);
+    a.M = M;
+    a.x_bf16 = e->act; a.xb_ld = e->inter_l;
+    if (!tp) {
+      a.out_f32 = x; a.out_ld = c.hidden;
+      TRY((launch_gemm<PRO_BF16, EPI_RESID>(e, e->p_d, a)));
+    } else {
+      a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
+      TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_d, a)));
+      NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+      CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
+    }
+  }
+  return LSK_OK;
+}
+
+// final RMSNorm + LM head on rows [row0, row0+M): arg-max candidates (and optional logits).
+// (llama_model_utils.py:204-205, 271-273, 386-387).  Afterwards e->cand_* / n_cand() hold one
+// (value, index) per candidate per row.
+static int enqueue_lm_head(lsk_engine* e, int row0, int M) {
+  const lsk_config& c = e->cfg;
+  GemmArgs a{};
+  a.W = reinterpret_cast<const uint4*>(e->lm_head);
+  a.M = M;
+  a.x_f32 = e->hidden + (size_t)row0 * c.hidden; a.x_ld = c.hidden;
+  a.norm_w = e->final_norm; a.eps = c.rms_eps;
+  a.logits = e->keep_logits ? e->logits : nullptr; a.logits_ld = e->vocab_l_pad;
+  a.n_valid_rows = e->vocab_l; a.vocab_off = e->vocab_off;
+  a.part_val = e->cand_val; a.part_idx = e->cand_idx;
+  TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
+  if (c.tp_size > 1) {
+    CU(launch(e, rank_best_kernel, dim3(1), dim3(256), 0, (const float*)e->cand_val,
+              (const int*)e->cand_idx, e->lm_cand, M, e->rank_val, e->rank_idx));
+    NC(ncclAllGather(e->rank_val, e->gath_val, kMaxRows, ncclFloat, e->comm, e->stream));
+    NC(ncclAllGather(e->rank_idx, e->gath_idx, kMaxRows, ncclInt32, e->comm, e->stream));
+  }
+  return LSK_OK;
+}
+static const float* cand_val_ptr(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->gath_val : e->cand_val; }
+static const int* cand_idx_ptr(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->gath_idx : e->cand_idx; }
+static int n_cand(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->cfg.tp_size : e->lm_cand; }
+
+// ---------------------------------------------------------------------------------------------
+// round / AR-step command streams
+// ---------------------------------------------------------------------------------------------
+static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
+  const lsk_config& c = e->cfg;
+  const int* len = &e->state->len;
+  // row 0 <- embedding of the pending token (self_speculation_generator.py:122, input_ids)
+  CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+            (const int*)&e->state->tok[0], e->hidden, c.hidden));
+  // draft loop (:127-148): step i runs layers [0,E) on row i at position len+i, then the shared
+  // head; its arg-max becomes tok[i+1] and is embedded into row i+1.
+  for (int i = 0; i < d; ++i) {
+    for (int l = 0; l < E; ++l) TRY(enqueue_layer(e, l, i, 1, len, i));
+    TRY(enqueue_lm_head(e, i, 1));
+    CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
+              e->state, 1 + i, (const __nv_bfloat16*)e->embed, c.hidden,
+              e->hidden + (size_t)(i + 1) * c.hidden));
+  }
+  // verify (:164-174 -> llama_model_utils.py:280-391): the last drafted token has not been
+  // through layers < E yet (:350-362) ...
+  for (int l = 0; l < E; ++l) TRY(enqueue_layer(e, l, d, 1, len, d));
+  // ... then layers >= E see [exit rows of the draft steps ; that row] = rows 0..d (:363-383)
+  for (int l = E; l < c.n_layers; ++l) TRY(enqueue_layer(e, l, 0, d + 1, len, 0));
+  TRY(enqueue_lm_head(e, 0, d + 1));
+  CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d,
+            e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
+  return LSK_OK;
+}
+
+static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
+  const lsk_config& c = e->cfg;
+  const int* len = &e->state->len;
+  CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+            (const int*)&e->state->tok[0], e->hidden, c.hidden));
+  for (int l = 0; l < n_layers_run; ++l) TRY(enqueue_layer(e, l, 0, 1, len, 0));
+  TRY(enqueue_lm_head(e, 0, 1));
+  CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
+            e->res_dev, seq));
+  return LSK_OK;
+}
+
+// Run `enqueue` either eagerly or as a cached CUDA graph keyed by `key`.  The completion stamp
+// (`seq`) is baked into eager launches; graph replays use stamp 0 + an event instead.
+template <typename F>
+static int run_cached(lsk_engine* e, long long key, F enqueue) {
+  CU(cudaEventRecord(e->ev0, e->stream));
+  if (!e->use_graph) {
+    TRY(enqueue());
+  } else {
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      const int64_t before = e->launches;
+      e->capture_launches = 0;
+      CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      int st = enqueue();
+      cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+      if (st != LSK_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+      if (ce != cudaSuccess) return fail(LSK_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      cudaGraphExec_t exec = nullptr;
+      CU(cudaGraphInstantiate(&exec, graph, 0));
+      CU(cudaGraphDestroy(graph));
+      e->graph_launches[key] = e->capture_launches;
+      e->launches = before;   // captured, not executed
+      it = e->graphs.emplace(key, exec).first;
+    }
+    CU(cudaGraphLaunch(it->second, e->stream));
+    e->launches += e->graph_launches[key];
+  }
+  CU(cudaEventRecord(e->ev1, e->stream));
+  CU(cudaEventSynchronize(e->ev1));
+  CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  return LSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int lsk_abi_version(void) { return LSK_ABI_VERSION; }
+const char* lsk_last_error(void) { return g_last_error.c_str(); }
+
+int lsk_create(const lsk_config* cfg, lsk_engine** out) {
+  if (!cfg || !out) return fail(LSK_ERR_INVALID, "null argument");
+  const lsk_config& c = *cfg;
+  if (c.head_dim != kHeadDim) return fail(LSK_ERR_INVALID, "head_dim %d unsupported (kernels are specialised for 128)", c.head_dim);
+  if (c.tp_size < 1 || c.tp_rank < 0 || c.tp_rank >= c.tp_size) return fail(LSK_ERR_INVALID, "bad tp_rank/tp_size");
+  if (c.n_heads % c.tp_size || c.n_kv_heads % c.tp_size || c.n_heads % c.n_kv_heads)
+    return fail(LSK_ERR_INVALID, "heads (%d) / kv heads (%d) must divide by tp_size (%d)", c.n_heads, c.n_kv_heads, c.tp_size);
+  if (c.inter % (c.tp_size * 32)) return fail(LSK_ERR_INVALID, "intermediate size %d must be a multiple of 32*tp_size", c.inter);
+  if (c.hidden % 32 || c.hidden > 8192) return fail(LSK_ERR_INVALID, "hidden %d must be a multiple of 32 and <= 8192", c.hidden);
+  if (c.vocab % c.tp_size) return fail(LSK_ERR_INVALID, "vocab must divide by tp_size");
+  if (c.n_layers < 1 || c.max_ctx < 2) return fail(LSK_ERR_INVALID, "bad n_layers / max_ctx");
+
+  lsk_engine* e = new lsk_engine();
+  e->cfg = c;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  e->use_pdl = !(c.flags & LSK_FLAG_NO_PDL);
+  e->use_graph = !(c.flags & LSK_FLAG_NO_GRAPH);
+  e->keep_logits = (c.flags & LSK_FLAG_KEEP_LOGITS) != 0;
+  e->heads_l = c.n_heads / c.tp_size;
+  e->kv_heads_l = c.n_kv_heads / c.tp_size;
+  e->group = c.n_heads / c.n_kv_heads;
+  e->q_rows = e->heads_l * kHeadDim;
+  e->kv_rows = e->kv_heads_l * kHeadDim;
+  e->inter_l = c.inter / c.tp_size;
+  e->vocab_l = c.vocab / c.tp_size;
+  e->vocab_l_pad = (e->vocab_l + 15) / 16 * 16;
+  e->vocab_off = c.tp_rank * e->vocab_l;
+  e->n_pages = (c.max_ctx + kPageTokens - 1) / kPageTokens;
+  e->max_pos = e->n_pages * kPageTokens;
+  e->n_splits = c.attn_splits > 0 ? c.attn_splits : (e->sm_count + e->kv_heads_l - 1) / e->kv_heads_l;
+  if (e->n_splits > 16) e->n_splits = 16;
+  if (e->n_splits < 1) e->n_splits = 1;
+
+  e->p_qkv = make_plan(e->q_rows + 2 * e->kv_rows, c.hidden, e->sm_count);
+  e->p_o = make_plan(c.hidden, e->q_rows, e->sm_count);
+  e->p_gu = make_plan(2 * e->inter_l, c.hidden, e->sm_count);
+  e->p_d = make_plan(c.hidden, e->inter_l, e->sm_count);
+  e->p_lm = make_plan(e->vocab_l_pad, c.hidden, e->sm_count);
+  e->lm_cand = e->p_lm.grid;
+  if (gemm_smem_bytes<1>(e->inter_l, EPI_RESID, e->p_d.ks_log2) > (size_t)kSmemMax)
+    return fail(LSK_ERR_INVALID, "intermediate size per rank (%d) too large for the resident-activation down projection", e->inter_l);
+
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&e->ev0));
+  CU(cudaEventCreate(&e->ev1));
+
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    cudaError_t er = cudaMalloc(p, bytes);
+    if (er != cudaSuccess) return fail(LSK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(er));
+    cudaMemsetAsync(*p, 0, bytes, e->stream);
+    return LSK_OK;
+  };
+  const size_t h = c.hidden;
+  e->layers.resize(c.n_layers);
+  for (auto& L : e->layers) {
+    TRY(alloc((void**)&L.wqkv, (size_t)(e->q_rows + 2 * e->kv_rows) * h * 2));
+    TRY(alloc((void**)&L.wo, h * e->q_rows * 2));
+    TRY(alloc((void**)&L.wgu, (size_t)2 * e->inter_l * h * 2));
+    TRY(alloc((void**)&L.wd, h * e->inter_l * 2));
+    TRY(alloc((void**)&L.ln1, h * 2));
+    TRY(alloc((void**)&L.ln2, h * 2));
+  }
+  TRY(alloc((void**)&e->embed, (size_t)c.vocab * h * 2));
+  TRY(alloc((void**)&e->final_norm, h * 2));
+  TRY(alloc((void**)&e->lm_head, (size_t)e->vocab_l_pad * h * 2));
+  e->pool_layer_elems = (size_t)e->n_pages * e->kv_heads_l * kPageTokens * kHeadDim;
+  TRY(alloc((void**)&e->kpool, e->pool_layer_elems * c.n_layers * 2));
+  TRY(alloc((void**)&e->vpool, e->pool_layer_elems * c.n_layers * 2));
+  TRY(alloc((void**)&e->page_table, (size_t)e->n_pages * 4));
+  TRY(alloc((void**)&e->rope, (size_t)e->max_pos * 64 * sizeof(float2)));
+  TRY(alloc((void**)&e->hidden, (size_t)(kMaxRows + 1) * h * 4));
+  TRY(alloc((void**)&e->qbuf, (size_t)kMaxRows * e->q_rows * 2));
+  TRY(alloc((void**)&e->attn_out, (size_t)kMaxRows * e->q_rows * 2));
+  TRY(alloc((void**)&e->act, (size_t)kMaxRows * e->inter_l * 2));
+  TRY(alloc((void**)&e->tp_buf, (size_t)kMaxRows * h * 4));
+  if (e->keep_logits) TRY(alloc((void**)&e->logits, (size_t)kMaxRows * e->vocab_l_pad * 4));
+  TRY(alloc((void**)&e->cand_val, (size_t)e->sm_count * kMaxRows * 4));
+  TRY(alloc((void**)&e->cand_idx, (size_t)e->sm_count * kMaxRows * 4));
+  TRY(alloc((void**)&e->gath_val, (size_t)c.tp_size * kMaxRows * 4));
+  TRY(alloc((void**)&e->gath_idx, (size_t)c.tp_size * kMaxRows * 4));
+  TRY(alloc((void**)&e->rank_val, kMaxRows * 4));
+  TRY(alloc((void**)&e->rank_idx, kMaxRows * 4));
+  const size_t prow = (size_t)e->kv_heads_l * e->n_splits * e->group * 16;
+  TRY(alloc((void**)&e->part_o, prow * kHeadDim * 4));
+  TRY(alloc((void**)&e->part_ml, prow * 2 * 4));
+  TRY(alloc((void**)&e->tickets, (size_t)e->kv_heads_l * 4));
+  TRY(alloc((void**)&e->d_zero, 4));
+  TRY(alloc((void**)&e->d_prompt, (size_t)e->max_pos * 4));
+  TRY(alloc((void**)&e->state, sizeof(DevState)));
+  TRY(alloc((void**)&e->gen_dev, sizeof(GenParams)));
+  CU(cudaHostAlloc((void**)&e->res_host, sizeof(RoundResult), cudaHostAllocMapped));
+  memset(e->res_host, 0, sizeof(RoundResult));
+  CU(cudaHostGetDevicePointer((void**)&e->res_dev, e->res_host, 0));
+
+  {  // identity page table + RoPE table (fp32 maths as HF: inv_freq, angle and cos/sin in fp32)
+    std::vector<int> pt(e->n_pages);
+    for (int i = 0; i < e->n_pages; ++i) pt[i] = i;
+    CU(cudaMemcpyAsync(e->page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    std::vector<float2> tab((size_t)e->max_pos * 64);
+    for (int d = 0; d < 64; ++d) {
+      const float inv_freq = 1.0f / powf(c.rope_theta, (float)(2 * d) / (float)kHeadDim);
+      for (int p = 0; p < e->max_pos; ++p) {
+        const float ang = (float)p * inv_freq;
+        tab[(size_t)p * 64 + d] = make_float2((float)cos((double)ang), (float)sin((double)ang));
+      }
+    }
+    CU(cudaMemcpyAsync(e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  *out = e;
+  return LSK_OK;
+}
+
+void lsk_destroy(lsk_engine* e) {
+  if (!e) return;
+  cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  if (e->comm) ncclCommDestroy(e->comm);
+  for (auto& L : e->layers) {
+    cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
+  }
+  void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->kpool, e->vpool, e->page_table, e->rope,
+                  e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->cand_val,
+                  e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx, e->part_o,
+                  e->part_ml, e->tickets, e->d_zero, e->d_prompt, e->state, e->gen_dev};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (e->res_host) cudaFreeHost(e->res_host);
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int lsk_comm_unique_id(uint8_t id_out[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  memcpy(id_out, &id, 128);
+  return LSK_OK;
+}
+
+int lsk_comm_init(lsk_engine* e, const uint8_t id_in[128]) {
+  if (!e) return fail(LSK_ERR_INVALID, "null engine");
+  if (e->cfg.tp_size == 1) return LSK_OK;
+  ncclUniqueId id;
+  memcpy(&id, id_in, 128);
+  NC(ncclCommInitRank(&e->comm, e->cfg.tp_size, id, e->cfg.tp_rank));
+  return LSK_OK;
+}
+
+static int pack(lsk_engine* e, const __nv_bfloat16* src, int64_t src_ld, int64_t row0, int64_t col0,
+                int64_t n_rows, int64_t K, __nv_bfloat16* dst, int64_t dst_row0, int mode) {
+  const int64_t pairs = n_rows * (K / 2);
+  int blocks = (int)((pairs + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  pack_rows_kernel<<<blocks, 256, 0, e->stream>>>(src, src_ld, row0, col0, n_rows, K, dst, dst_row0, mode);
+  CU(cudaGetLastError());
+  return LSK_OK;
+}
+
+int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n) {
+  if (!e || !descs) return fail(LSK_ERR_INVALID, "null argument");
+  const lsk_config& c = e->cfg;
+  const int r = c.tp_rank;
+  for (int i = 0; i < n; ++i) {
+    const lsk_weight_desc& d = descs[i];
+    const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(d.data);
+    auto expect = [&](int64_t rows, int64_t cols) -> int {
+      if (d.rows != rows || d.cols != cols)
+        return fail(LSK_ERR_INVALID, "weight role %d layer %d: shape [%lld,%lld], expected [%lld,%lld]",
+                    d.role, d.layer, (long long)d.rows, (long long)d.cols, (long long)rows, (long long)cols);
+      return LSK_OK;
+    };
+    const bool per_layer = d.role >= LSK_W_LN1;
+    if (per_layer && (d.layer < 0 || d.layer >= c.n_layers)) return fail(LSK_ERR_INVALID, "bad layer %d", d.layer);
+    LayerWeights* L = per_layer ? &e->layers[d.layer] : nullptr;
+    const int64_t h = c.hidden, qd = (int64_t)c.n_heads * kHeadDim, kvd = (int64_t)c.n_kv_heads * kHeadDim;
+    switch (d.role) {
+      case LSK_W_EMBED:
+        TRY(expect(c.vocab, h));
+        CU(cudaMemcpyAsync(e->embed, src, (size_t)c.vocab * h * 2, cudaMemcpyDeviceToDevice, e->stream));
+        e->globals_loaded |= 1u;
+        break;
+      case LSK_W_FINAL_NORM:
+        TRY(expect(h, 1));
+        CU(cudaMemcpyAsync(e->final_norm, src, h * 2, cudaMemcpyDeviceToDevice, e->stream));
+        e->globals_loaded |= 2u;
+        break;
+      case LSK_W_LM_HEAD:
+        TRY(expect(c.vocab, h));
+        TRY(pack(e, src, h, (int64_t)r * e->vocab_l, 0, e->vocab_l, h, e->lm_head, 0, MAP_PLAIN));
+        e->globals_loaded |= 4u;
+        break;
+      case LSK_W_LN1:
+        TRY(expect(h, 1));
+        CU(cudaMemcpyAsync(L->ln1, src, h * 2, cudaMemcpyDeviceToDevice, e->stream));
+        break;
+      case LSK_W_LN2:
+        TRY(expect(h, 1));
+        CU(cudaMemcpyAsync(L->ln2, src, h * 2, cudaMemcpyDeviceToDevice, e->stream));
+        break;
+      case LSK_W_Q:
+        TRY(expect(qd, h));
+        TRY(pack(e, src, h, (int64_t)r * e->q_rows, 0, e->q_rows, h, L->wqkv, 0, MAP_ROPE_HEADS));
+        break;
+      case LSK_W_K:
+        TRY(expect(kvd, h));
+        TRY(pack(e, src, h, (int64_t)r * e->kv_rows, 0, e->kv_rows, h, L->wqkv, e->q_rows, MAP_ROPE_HEADS));
+        break;
+      case LSK_W_V:
+        TRY(expect(kvd, h));
+        TRY(pack(e, src, h, (int64_t)r * e->kv_rows, 0, e->kv_rows, h, L->wqkv, e->q_rows + e->kv_rows, MAP_PLAIN));
+        break;
+      case LSK_W_O:   // row-parallel: this rank's input features = its heads
+        TRY(expect(h, qd));
+        TRY(pack(e, src, qd, 0, (int64_t)r * e->q_rows, h, e->q_rows, L->wo, 0, MAP_PLAIN));
+        break;
+      case LSK_W_GATE:
+        TRY(expect(c.inter, h));
+        TRY(pack(e, src, h, (int64_t)r * e->inter_l, 0, e->inter_l, h, L->wgu, 0, MAP_GATE));
+        break;
+      case LSK_W_UP:
+        TRY(expect(c.inter, h));
+        TRY(pack(e, src, h, (int64_t)r * e->inter_l, 0, e->inter_l, h, L->wgu, 0, MAP_UP));
+        break;
+      case LSK_W_DOWN:
+        TRY(expect(h, c.inter));
+        TRY(pack(e, src, c.inter, 0, (int64_t)r * e->inter_l, h, e->inter_l, L->wd, 0, MAP_PLAIN));
+        break;
+      default:
+        return fail(LSK_ERR_INVALID, "unknown weight role %d", d.role);
+    }
+    if (L) L->loaded |= 1u << d.role;
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return LSK_OK;
+}
+
+int lsk_weights_complete(const lsk_engine* e) {
+  if (!e) return 0;
+  if (e->globals_loaded != 7u) return 0;
+  const unsigned need = (1u << LSK_W_LN1) | (1u << LSK_W_Q) | (1u << LSK_W_K) | (1u << LSK_W_V) |
+                        (1u << LSK_W_O) | (1u << LSK_W_LN2) | (1u << LSK_W_GATE) | (1u << LSK_W_UP) |
+                        (1u << LSK_W_DOWN);
+  for (const auto& L : e->layers)
+    if ((L.loaded & need) != need) return 0;
+  return 1;
+}
+
+int lsk_begin(lsk_engine* e, const lsk_generation* gen) {
+  if (!e || !gen) return fail(LSK_ERR_INVALID, "null argument");
+  if (!lsk_weights_complete(e)) return fail(LSK_ERR_STATE, "weights not fully loaded");
+  if (gen->n_eos < 0 || gen->n_eos > LSK_MAX_EOS) return fail(LSK_ERR_INVALID, "n_eos out of range");
+  if (gen->exit_layer > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "exit_layer > n_layers");
+  if (gen->sample) return fail(LSK_ERR_INVALID, "sampling path not available in this build (greedy only)");
+  e->gen = *gen;
+  GenParams gp{};
+  gp.n_eos = gen->n_eos;
+  for (int i = 0; i < gen->n_eos; ++i) gp.eos[i] = gen->eos_ids[i];
+  gp.sample = gen->sample; gp.temperature = gen->temperature; gp.top_k = gen->top_k; gp.top_p = gen->top_p;
+  gp.seed = gen->seed;
+  CU(cudaMemcpyAsync(e->gen_dev, &gp, sizeof(gp), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemsetAsync(e->state, 0, sizeof(DevState), e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->began = true;
+  e->prefilled = false;
+  e->host_len = 0;
+  return LSK_OK;
+}
+
+int lsk_prefill(lsk_engine* e, const int32_t* ids, int32_t n) {
+  if (!e || !ids) return fail(LSK_ERR_INVALID, "null argument");
+  if (!e->began) return fail(LSK_ERR_STATE, "lsk_begin must precede lsk_prefill");
+  if (n < 1) return fail(LSK_ERR_INVALID, "empty prompt");
+  if (n + 1 > e->cfg.max_ctx) return fail(LSK_ERR_CTX, "prompt of %d tokens exceeds max_ctx %d", n, e->cfg.max_ctx);
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= e->cfg.vocab) return fail(LSK_ERR_INVALID, "token id %d out of range", ids[i]);
+  const lsk_config& c = e->cfg;
+  CU(cudaEventRecord(e->ev0, e->stream));
+  CU(cudaMemcpyAsync(e->d_prompt, ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  // ids[0 .. n-2] through every layer in blocks of <= 16 rows; no LM head: the reference
+  // discards those logits too (self_speculation_generator.py:177).
+  for (int c0 = 0; c0 < n - 1; c0 += kMaxRows) {
+    const int m = (n - 1 - c0) < kMaxRows ? (n - 1 - c0) : kMaxRows;
+    CU(launch(e, embed_tokens_kernel, dim3(m), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+              (const int*)(e->d_prompt + c0), e->hidden, c.hidden));
+    for (int l = 0; l < c.n_layers; ++l) TRY(enqueue_layer(e, l, 0, m, e->d_zero, c0));
+  }
+  set_state_kernel<<<1, 1, 0, e->stream>>>(e->state, n - 1, ids[n - 1], 0);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(e->ev1, e->stream));
+  CU(cudaEventSynchronize(e->ev1));
+  CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  e->host_len = n - 1;
+  e->prefilled = true;
+  return LSK_OK;
+}
+
+static void copy_result(const lsk_engine* e, lsk_round_out* out) {
+  const RoundResult& r = *e->res_host;
+  out->n_drafted = r.n_drafted;
+  out->n_matches = r.n_matches;
+  out->n_emitted = r.n_emitted;
+  out->kv_len = r.kv_len;
+  for (int i = 0; i < kMaxRows; ++i) {
+    out->draft_ids[i] = r.draft_ids[i];
+    out->emitted_ids[i] = r.emitted_ids[i];
+    out->verified_ids[i] = r.verified_ids[i];
+  }
+}
+
+int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
+  if (!e || !out) return fail(LSK_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_round");
+  if (d_req < 0 || d_req > LSK_MAX_SPEC) return fail(LSK_ERR_INVALID, "d_req %d out of [0,%d]", d_req, LSK_MAX_SPEC);
+  const int E = e->gen.exit_layer;
+  if (E < 1 || E > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "self-speculation needs 1 <= exit_layer <= n_layers (got %d)", E);
+  if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context %d + %d exceeds max_ctx", e->host_len, d_req + 1);
+  const int seq = ++e->seq;
+  const long long key = ((long long)E << 20) | ((long long)d_req << 8) | 1;
+  TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
+  (void)seq;
+  copy_result(e, out);
+  e->host_len = out->kv_len;
+  return LSK_OK;
+}
+
+int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
+  if (!e || !token_out) return fail(LSK_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_ar_step");
+  if (e->host_len + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
+  const int nl = (e->gen.exit_layer > 0 && e->gen.exit_layer <= e->cfg.n_layers) ? e->gen.exit_layer : e->cfg.n_layers;
+  const long long key = ((long long)nl << 20) | 2;
+  TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
+  *token_out = e->res_host->emitted_ids[0];
+  e->host_len = e->res_host->kv_len;
+  return LSK_OK;
+}
+
+int lsk_kv_len(const lsk_engine* e, int32_t* len_out) {
+  if (!e || !len_out) return fail(LSK_ERR_INVALID, "null argument");
+  *len_out = e->host_len;
+  return LSK_OK;
+}
+
+int lsk_debug_set_page_table(lsk_engine* e, const int32_t* pages, int32_t n) {
+  if (!e || !pages || n != e->n_pages) return fail(LSK_ERR_INVALID, "page table must have %d entries", e ? e->n_pages : 0);
+  std::vector<char> seen(n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (pages[i] < 0 || pages[i] >= n || seen[pages[i]]) return fail(LSK_ERR_INVALID, "page table is not a permutation");
+    seen[pages[i]] = 1;
+  }
+  CU(cudaMemcpyAsync(e->page_table, pages, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return LSK_OK;
+}
+
+int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index, float* dst, int64_t n) {
+  if (!e || !dst) return fail(LSK_ERR_INVALID, "null argument");
+  CU(cudaStreamSynchronize(e->stream));
+  if (what == LSK_DBG_HIDDEN) {
+    if (n > (int64_t)kMaxRows * e->cfg.hidden) return fail(LSK_ERR_INVALID, "too many floats");
+    CU(cudaMemcpy(dst, e->hidden, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return LSK_OK;
+  }
+  if (what == LSK_DBG_LOGITS) {
+    if (!e->keep_logits) return fail(LSK_ERR_STATE, "engine created without LSK_FLAG_KEEP_LOGITS");
+    if (n > (int64_t)kMaxRows * e->vocab_l_pad) return fail(LSK_ERR_INVALID, "too many floats");
+    CU(cudaMemcpy(dst, e->logits, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return LSK_OK;
+  }
+  if (what == LSK_DBG_KROW || what == LSK_DBG_VROW) {
+    if (layer < 0 || layer >= e->cfg.n_layers || n != kHeadDim) return fail(LSK_ERR_INVALID, "bad layer / n");
+    const int64_t head = index / e->cfg.max_ctx, pos = index % e->cfg.max_ctx;
+    if (head >= e->kv_heads_l) return fail(LSK_ERR_INVALID, "bad kv head");
+    std::vector<int> pt(e->n_pages);
+    CU(cudaMemcpy(pt.data(), e->page_table, pt.size() * 4, cudaMemcpyDeviceToHost));
+    const __nv_bfloat16* pool = (what == LSK_DBG_KROW ? e->kpool : e->vpool) + (size_t)layer * e->pool_layer_elems;
+    const __nv_bfloat16* src = pool + ((size_t)(pt[pos >> 6] * e->kv_heads_l + head) * kPageTokens + (pos & 63)) * kHeadDim;
+    std::vector<__nv_bfloat16> tmp(kHeadDim);
+    CU(cudaMemcpy(tmp.data(), src, kHeadDim * 2, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < kHeadDim; ++i) dst[i] = __bfloat162float(tmp[i]);
+    return LSK_OK;
+  }
+  return fail(LSK_ERR_INVALID, "unknown debug selector %d", what);
+}
+
+// algorithmic bytes, per GPU: packed weights streamed once per layer call,
+// LM head once per head call, KV entries of the visible context once per layer call.
+static double layer_weight_bytes(const lsk_engine* e) {
+  const double h = e->cfg.hidden;
+  return 2.0 * ((double)(e->q_rows + 2 * e->kv_rows) * h + h * e->q_rows + 3.0 * e->inter_l * h);
+}
+int lsk_round_bytes(const lsk_engine* e, int32_t d, int32_t ctx, double* out) {
+  if (!e || !out) return fail(LSK_ERR_INVALID, "null argument");
+  const int E = e->gen.exit_layer, L = e->cfg.n_layers;
+  const double wl = layer_weight_bytes(e), wh = 2.0 * e->vocab_l * e->cfg.hidden;
+  const double kv_tok = 2.0 * 2.0 * e->kv_rows;
+  const double layer_calls = (double)(d + 1) * E + (L - E);
+  *out = layer_calls * wl + (d + 1) * wh + layer_calls * ctx * kv_tok;
+  return LSK_OK;
+}
+int lsk_ar_bytes(const lsk_engine* e, int32_t ctx, double* out) {
+  if (!e || !out) return fail(LSK_ERR_INVALID, "null argument");
+  const int nl = (e->gen.exit_layer > 0) ? e->gen.exit_layer : e->cfg.n_layers;
+  *out = nl * (layer_weight_bytes(e) + ctx * 2.0 * 2.0 * e->kv_rows) + 2.0 * e->vocab_l * e->cfg.hidden;
+  return LSK_OK;
+}
+int lsk_launch_count(const lsk_engine* e, int64_t* out) {
+  if (!e || !out) return fail(LSK_ERR_INVALID, "null argument");
+  *out = e->launches;
+  return LSK_OK;
+}
+int lsk_last_device_ms(const lsk_engine* e, float* out) {
+  if (!e || !out) return fail(LSK_ERR_INVALID, "null argument");
+  *out = e->last_ms;
+  return LSK_OK;
+}
+
+// ---- stand-alone kernel entry points (unit tests / micro-benchmarks) ---------------------
+int lsk_test_pack(const void* w, int64_t n, int64_t k, void* packed) {
+  if (!w || !packed || n % 16 || k % 32) return fail(LSK_ERR_INVALID, "need n %% 16 == 0 and k %% 32 == 0");
+  const int64_t pairs = n * (k / 2);
+  int blocks = (int)((pairs + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_rows_kernel<<<blocks, 256>>>((const __nv_bfloat16*)w, k, 0, 0, n, k, (__nv_bfloat16*)packed, 0, MAP_PLAIN);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return LSK_OK;
+}
+
+int lsk_test_gemm(const void* packed, int64_t n, int64_t k, const void* x, int32_t m, float* y,
+                  int32_t iters, float* avg_ms) {
+  if (!packed || !x || !y || n % 16 || k % 32 || m < 1 || m > kMaxRows) return fail(LSK_ERR_INVALID, "bad gemm test shape");
+  lsk_engine tmp;   // only the launch plumbing is used
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&tmp.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  CU(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+  tmp.use_pdl = true;
+  GemmPlan p = make_plan((int)n, (int)k, tmp.sm_count);
+  GemmArgs a{};
+  a.W = (const uint4*)packed;
+  a.M = m;
+  a.x_bf16 = (const __nv_bfloat16*)x; a.xb_ld = (int)k;
+  a.out_f32 = y; a.out_ld = (int)n;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  int st = launch_gemm<PRO_BF16, EPI_STORE>(&tmp, p, a);   // warm-up + result
+  if (st != LSK_OK) return st;
+  CU(cudaStreamSynchronize(tmp.stream));
+  if (iters > 0) {
+    CU(cudaEventRecord(e0, tmp.stream));
+    for (int i = 0; i < iters; ++i) {
+      st = launch_gemm<PRO_BF16, EPI_STORE>(&tmp, p, a);
+      if (st != LSK_OK) return st;
+    }
+    CU(cudaEventRecord(e1, tmp.stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = ms / iters;
+  }
+  CU(cudaEventDestroy(e0));
+  CU(cudaEventDestroy(e1));
+  CU(cudaStreamDestroy(tmp.stream));
+  tmp.stream = nullptr;
+  return LSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Python handle on one liblsk engine (one per process / GPU).
+
+Host code here is plumbing only: it marshals arguments into the C ABI (include/lsk.h).  All
+arithmetic, the draft/verify/accept logic and the KV bookkeeping run in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .weights import LlamaArch, SyntheticLlama, iter_state_dict
+
+
+@dataclass
+class RoundOutput:
+    """One speculation round as seen by the host (lsk_round_out)."""
+    n_drafted: int
+    n_matches: int
+    emitted: List[int]
+    draft: List[int]
+    verified: List[int]
+    kv_len: int
+
+
+class Engine:
+    def __init__(self, arch: LlamaArch, max_ctx: int = 4096, tp_rank: int = 0, tp_size: int = 1,
+                 keep_logits: bool = False, use_pdl: bool = True, use_graph: bool = True,
+                 attn_splits: int = 0, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("layerskip_b200 needs a CUDA device (B200); there is no CPU path")
+        self._lib = _lib.load()
+        self.arch = arch
+        self.device = torch.device(device) if device is not None else \
+            torch.device("cuda", torch.cuda.current_device())
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        flags = (_lib.LSK_FLAG_KEEP_LOGITS if keep_logits else 0) | \
+                (0 if use_pdl else _lib.LSK_FLAG_NO_PDL) | (0 if use_graph else _lib.LSK_FLAG_NO_GRAPH)
+        cfg = _lib.lsk_config(
+            vocab=arch.vocab, hidden=arch.hidden, inter=arch.inter, n_layers=arch.layers,
+            n_heads=arch.heads, n_kv_heads=arch.kv_heads, head_dim=arch.head_dim,
+            rms_eps=arch.rms_eps, rope_theta=arch.rope_theta, max_ctx=max_ctx, tp_rank=tp_rank,
+            tp_size=tp_size, attn_splits=attn_splits, flags=flags)
+        self.max_ctx = max_ctx
+        self.keep_logits = keep_logits
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_create(C.byref(cfg), C.byref(handle)))
+        self._h = handle
+        self._exit_layer = -1
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            with torch.cuda.device(self.device):
+                self._lib.lsk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ tensor parallel
+    def init_comm(self, process_group=None) -> None:
+        """Create the engine's NCCL communicator; the unique id travels over torch.distributed
+        (plumbing only — the data path uses the engine's own communicator and stream)."""
+        if self.tp_size == 1:
+            return
+        import torch.distributed as dist
+        uid = (C.c_uint8 * 128)()
+        if self.tp_rank == 0:
+            _lib.check(self._lib.lsk_comm_unique_id(uid))
+        buf = torch.tensor(list(uid), dtype=torch.uint8)
+        backend = dist.get_backend(process_group)
+        if backend == "nccl":
+            buf = buf.to(self.device)
+        dist.broadcast(buf, src=dist.get_global_rank(process_group, 0) if process_group else 0,
+                       group=process_group)
+        arr = (C.c_uint8 * 128)(*buf.cpu().tolist())
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_comm_init(self._h, arr))
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, source: Iterable[Tuple[int, int, torch.Tensor]]) -> None:
+        with torch.cuda.device(self.device):
+            for role, layer, t in source:
+                assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()
+                # the tensor was produced on torch's stream; the engine packs on its own
+                torch.cuda.current_stream(self.device).synchronize()
+                rows = t.shape[0]
+                cols = t.shape[1] if t.dim() == 2 else 1
+                desc = _lib.lsk_weight_desc(role=role, layer=layer, data=t.data_ptr(), rows=rows,
+                                            cols=cols)
+                _lib.check(self._lib.lsk_load_weights(self._h, C.byref(desc), 1))
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.load_weights(iter_state_dict(sd, self.device))
+
+    def load_model(self, model) -> None:
+        """HF `LlamaForCausalLM` (any device / float dtype) or a `SyntheticLlama`."""
+        if isinstance(model, SyntheticLlama):
+            self.load_weights(model.iter_weights(self.device))
+        else:
+            self.load_state_dict(model.state_dict())
+        if not self._lib.lsk_weights_complete(self._h):
+            raise RuntimeError("model did not provide every tensor the engine needs")
+
+    # ------------------------------------------------------------------ generation
+    def begin(self, exit_layer: int, max_steps: int, eos_token_ids: Sequence[int],
+              sample: bool = False, temperature: float = 0.6, top_k: int = 0, top_p: float = 0.9,
+              seed: int = 0) -> None:
+        eos = list(eos_token_ids)
+        if len(eos) > _lib.LSK_MAX_EOS:
+            raise ValueError(f"at most {_lib.LSK_MAX_EOS} eos ids are supported")
+        gen = _lib.lsk_generation(exit_layer=exit_layer, max_steps=max_steps, n_eos=len(eos),
+                                  sample=int(bool(sample)), temperature=temperature, top_k=top_k,
+                                  top_p=top_p, seed=seed)
+        for i, t in enumerate(eos):
+            gen.eos_ids[i] = int(t)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_begin(self._h, C.byref(gen)))
+        self._exit_layer = exit_layer
+
+    def prefill(self, prompt_ids: Sequence[int]) -> None:
+        n = len(prompt_ids)
+        arr = (C.c_int32 * n)(*[int(t) for t in prompt_ids])
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_prefill(self._h, arr, n))
+
+    def round(self, d_req: int) -> RoundOutput:
+        out = _lib.lsk_round_out()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_round(self._h, d_req, C.byref(out)))
+        return RoundOutput(
+            n_drafted=out.n_drafted, n_matches=out.n_matches,
+            emitted=list(out.emitted_ids[:out.n_emitted]),
+            draft=list(out.draft_ids[:out.n_drafted]),
+            verified=list(out.verified_ids[:out.n_drafted + 1]), kv_len=out.kv_len)
+
+    def ar_step(self) -> int:
+        tok = C.c_int32()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_ar_step(self._h, C.byref(tok)))
+        return tok.value
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def kv_len(self) -> int:
+        v = C.c_int32()
+        _lib.check(self._lib.lsk_kv_len(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        _lib.check(self._lib.lsk_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def last_device_ms(self) -> float:
+        v = C.c_float()
+        _lib.check(self._lib.lsk_last_device_ms(self._h, C.byref(v)))
+        return v.value
+
+    def round_bytes(self, d: int, ctx: int) -> float:
+        v = C.c_double()
+        _lib.check(self._lib.lsk_round_bytes(self._h, d, ctx, C.byref(v)))
+        return v.value
+
+    def ar_bytes(self, ctx: int) -> float:
+        v = C.c_double()
+        _lib.check(self._lib.lsk_ar_bytes(self._h, ctx, C.byref(v)))
+        return v.value
+
+    def debug_hidden(self, rows: int = 16) -> torch.Tensor:
+        n = rows * self.arch.hidden
+        buf = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_read(self._h, _lib.LSK_DBG_HIDDEN, 0, 0, buf, n))
+        return torch.tensor(list(buf), dtype=torch.float32).view(rows, self.arch.hidden)
+
+    def debug_logits(self, rows: int = 16) -> torch.Tensor:
+        vloc = self.arch.vocab // self.tp_size
+        vpad = (vloc + 15) // 16 * 16
+        n = rows * vpad
+        buf = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_read(self._h, _lib.LSK_DBG_LOGITS, 0, 0, buf, n))
+        return torch.frombuffer(buf, dtype=torch.float32).clone().view(rows, vpad)[:, :vloc]
+
+    def debug_kv_row(self, which: str, layer: int, kv_head: int, pos: int) -> torch.Tensor:
+        buf = (C.c_float * 128)()
+        what = _lib.LSK_DBG_KROW if which == "k" else _lib.LSK_DBG_VROW
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_read(self._h, what, layer, kv_head * self.max_ctx + pos,
+                                                buf, 128))
+        return torch.tensor(list(buf), dtype=torch.float32)
+
+    def debug_set_page_table(self, pages: Sequence[int]) -> None:
+        arr = (C.c_int32 * len(pages))(*[int(p) for p in pages])
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_set_page_table(self._h, arr, len(pages)))

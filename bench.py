@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py — tokens/s + acceptance rate of self-speculative decoding (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A STEP is one full generation: a 128-id synthetic prompt -> a 512-token greedy continuation,
+Llama-2-7B architecture, random-init weights (seeded), exit_layer 8, num_speculations 6 —
+BASELINE.json `configs[1]`.  Prefill is inside the timed region, exactly as the reference
+times it (self_speculation/generator_base.py:107-129).
+
+  value  : total generated tokens / device time (CUDA events on the engine's stream around
+           prefill and every round), inputs already resident on the device.
+  e2e    : the same generations timed by wall clock through the reference-facing plug-in call
+           `B200SelfSpeculativeGenerationStrategy.generate_token_ids` — host prompt ids in, host
+           token ids out, every host<->device copy and the per-round sync inside the region.
+  N > 1  : one process per GPU (torchrun).  The path is batch-1 decoding, so ranks are
+           independent replicas serving different prompts (weak scaling, no data-path
+           collective); `--tp` instead shards ONE model tensor-parallel over the N GPUs.
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port of
+/root/reference/self_speculation/*, which cannot travel to the GPU box) on the host cores, on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tokens_per_second_self_speculative_greedy"
+UNIT = "tokens/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="llama2-7b")
+    ap.add_argument("--exit-layer", type=int, default=8)
+    ap.add_argument("--num-speculations", type=int, default=6)
+    ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--max-steps", type=int, default=512)
+    ap.add_argument("--alpha", type=float, default=1.0,
+                    help="late-layer damping of the synthetic model (1.0 = pure random init)")
+    ap.add_argument("--tp", action="store_true", help="tensor-parallel over the N GPUs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the acceptance sweep / AR legs")
+    ap.add_argument("--cpu-max-steps", type=int, default=0, help="reference arm: tokens per step")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_weights(sd, arch):
+    """Oracle weights on the host: fp32 when RAM allows (torch's CPU bf16 matmul is an order of
+    magnitude slower than fp32 on these Xeons), else bf16."""
+    import psutil
+    import torch
+    from oracle import llama_oracle as orc
+    dims = orc.LlamaDims(vocab=arch.vocab, hidden=arch.hidden, inter=arch.inter,
+                         layers=arch.layers, heads=arch.heads, kv_heads=arch.kv_heads,
+                         head_dim=arch.head_dim, rms_eps=arch.rms_eps, rope_theta=arch.rope_theta)
+    need_fp32 = 2 * arch.param_bytes()
+    dtype = torch.float32 if psutil.virtual_memory().available > 1.5 * need_fp32 else torch.bfloat16
+    return orc.weights_from_state_dict(dims, sd, dtype=dtype), str(dtype).replace("torch.", "")
+
+
+def cpu_reference_run(args, w, arch, prompts, n_generations, max_steps):
+    """Time `n_generations` greedy self-speculative generations of `max_steps` tokens with the
+    oracle (CPU restatement of the reference algorithm).  Returns (tokens, seconds, acc)."""
+    import torch
+    from oracle import llama_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    tokens, seconds, rates = 0, 0.0, []
+    with torch.inference_mode():
+        for i in range(n_generations):
+            prompt = prompts[i % len(prompts)]
+            t0 = time.perf_counter()
+            res = orc.self_speculative_generate(
+                w, prompt, [arch.vocab - 1], max_steps=max_steps, exit_layer=args.exit_layer,
+                num_speculations=args.num_speculations, sample=False)
+            seconds += time.perf_counter() - t0
+            tokens += len(res.predicted_tokens)
+            rates.append(res.acceptance_rate)
+    return tokens, seconds, sum(rates) / max(1, len(rates))
+
+
+def cpu_sized_sample(args, w, arch, prompts, budget_s):
+    """Pick a continuation length so one generation costs about `budget_s` of CPU time:
+    probe with 2 tokens (prefill + 1-2 rounds), then extrapolate the per-round cost."""
+    t0 = time.perf_counter()
+    cpu_reference_run(args, w, arch, prompts, 1, 2)
+    probe = time.perf_counter() - t0
+    # a 2-token probe is prefill + <= 2 rounds; assume half of it is per-round cost (upper bound)
+    per_round = max(probe / 4, 1e-3)
+    n = int(max(2, min(64, (budget_s - probe) / per_round)))
+    return n, probe
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from layerskip_b200.synthetic import synthetic_prompts
+    from layerskip_b200.weights import ARCHS, SyntheticLlama
+    arch = ARCHS[args.arch]
+    dev = "cuda" if torch.cuda.is_available() else "cpu"   # RNG only: none of our kernels
+    model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=args.exit_layer, device=dev)
+    sd = model.state_dict(dtype=torch.bfloat16, device="cpu")
+    prompts = synthetic_prompts(arch.vocab, 8, args.prompt_len)
+    cores = os.cpu_count() or 1
+    # bounded sample: same prompt length, a short continuation (CPU runs ~0.1-0.6 s per round)
+    w, w_dtype = cpu_weights(sd, arch)
+    del sd
+    budget = 120.0 / max(1, args.steps)           # whole arm: about two minutes of CPU time
+    cpu_steps, _probe = cpu_sized_sample(args, w, arch, prompts, budget)   # doubles as warm-up
+    if args.cpu_max_steps:
+        cpu_steps = args.cpu_max_steps
+    tokens, seconds, acc = cpu_reference_run(args, w, arch, prompts, max(1, args.steps), cpu_steps)
+    value = tokens / seconds
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / max(1, args.steps) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.arch} random-init alpha={args.alpha}, exit_layer={args.exit_layer}, "
+                               f"num_speculations={args.num_speculations}, greedy, prompt {args.prompt_len} ids",
+                   "sample": f"{cpu_steps}-token continuations (prefill of {args.prompt_len} ids included)"},
+        "acceptance_rate": acc,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "cpu": cpu_model_name(),
+                         "sample": f"{max(1, args.steps)} generations x {cpu_steps} tokens, "
+                                   f"prompt {args.prompt_len}, oracle port in torch {w_dtype} on {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from layerskip_b200 import GenerationConfig
+    from layerskip_b200.strategy import B200SelfSpeculativeGenerationStrategy
+    from layerskip_b200.synthetic import synthetic_prompts
+    from layerskip_b200.weights import ARCHS, SyntheticLlama
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    tp = world if (args.tp and world > 1) else 1
+
+    arch = ARCHS[args.arch]
+    model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=args.exit_layer, device="cuda")
+    max_ctx = ((args.prompt_len + args.max_steps + 64 + 63) // 64) * 64
+    strat = B200SelfSpeculativeGenerationStrategy(
+        max_ctx=max_ctx, tp_rank=rank if tp > 1 else 0, tp_size=tp)
+    eng = strat.engine_for(model)
+    prompts = synthetic_prompts(arch.vocab, 8 * max(1, world), args.prompt_len)
+    if tp == 1:
+        prompts = prompts[rank::world]       # replicas: disjoint prompt streams per GPU
+    gcfg = GenerationConfig(max_steps=args.max_steps, exit_layer=args.exit_layer,
+                            num_speculations=args.num_speculations, sample=False,
+                            generation_strategy="self_speculative")
+    eos = [arch.vocab - 1]
+
+    def one_generation(i):
+        """Returns (tokens, device_ms, wall_s, acceptance, bytes)."""
+        prompt = prompts[i % len(prompts)]
+        dev_ms = 0.0
+        alg_bytes = 0.0
+        # device-timed leg: identical calls, timed with the engine's CUDA events
+        eng.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
+        eng.prefill(prompt)
+        dev_ms += eng.last_device_ms
+        out, matches, drafted = [], 0, 0
+        while len(out) < args.max_steps:
+            d = min(args.num_speculations, args.max_steps - len(out) - 1)
+            ctx = eng.kv_len
+            r = eng.round(d)
+            dev_ms += eng.last_device_ms
+            alg_bytes += eng.round_bytes(d, ctx)
+            out += r.emitted
+            matches += r.n_matches
+            drafted += r.n_drafted
+            if eos[0] in out:
+                out = out[: out.index(eos[0])]
+                break
+        return len(out), dev_ms, matches / max(1, drafted), alg_bytes, len(out)
+
+    def one_generation_e2e(i):
+        prompt = prompts[i % len(prompts)]
+        t0 = time.perf_counter()
+        res = strat.generate_token_ids(model, prompt, eos, gcfg)
+        return len(res.predicted_tokens), time.perf_counter() - t0, len(strat.last_rounds)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_generation(i)
+    barrier()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    tok_dev = 0
+    dev_ms_total = 0.0
+    bytes_total = 0.0
+    accs = []
+    for i in range(args.steps):
+        n, ms, acc, b, _ = one_generation(args.warmup + i)
+        tok_dev += n
+        dev_ms_total += ms
+        bytes_total += b
+        accs.append(acc)
+    barrier()
+    launches = eng.launch_count - launches0
+    # e2e leg through the plug-in call (wall clock, host buffers)
+    tok_e2e, wall_total, rounds_total = 0, 0.0, 0
+    for i in range(args.steps):
+        n, s, nr = one_generation_e2e(args.warmup + i)
+        tok_e2e += n
+        wall_total += s
+        rounds_total += nr
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_dev = allmax(dev_ms_total) * 1e-3
+    t_wall = allmax(wall_total)
+    if tp > 1:        # every rank holds the same stream of tokens
+        tokens_total, tokens_total_e2e = tok_dev, tok_e2e
+    else:
+        tokens_total, tokens_total_e2e = allsum(tok_dev), allsum(tok_e2e)
+    value = tokens_total / t_dev
+    e2e_value = tokens_total_e2e / t_wall
+
+    # ---- roofline of the dominant kernel (weight-streaming skinny GEMM), measured live
+    peak, peak_kind = measured_peaks()
+    roof = None
+    extra = {}
+    if rank == 0:
+        eng.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
+        eng.prefill(prompts[0])
+        for _ in range(2):
+            eng.round(args.num_speculations)
+        cls_ms = {k: 0.0 for k in eng.KERNEL_CLASSES}
+        cls_n = {k: 0 for k in eng.KERNEL_CLASSES}
+        reps = 5
+        for _ in range(reps):
+            _r, ms, cnt, _tot = eng.profile_round(args.num_speculations)
+            for k in ms:
+                cls_ms[k] += ms[k]
+                cls_n[k] += cnt[k]
+        a = arch
+        t = max(1, tp)
+        wb = {"qkv": 2.0 * (a.q_dim + 2 * a.kv_dim) * a.hidden / t, "o_proj": 2.0 * a.hidden * a.q_dim / t,
+              "gate_up": 2.0 * 2 * a.inter * a.hidden / t, "down": 2.0 * a.hidden * a.inter / t,
+              "lm_head": 2.0 * a.vocab * a.hidden / t}
+        gemm_bytes = sum(wb[k] * cls_n[k] for k in wb)
+        gemm_ms = sum(cls_ms[k] for k in wb)
+        gemm_launches = sum(cls_n[k] for k in wb)
+        achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "lsk::gemm_skinny_kernel<NT,PRO,EPI> (all GEMM launches of a round)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                "bytes_per_launch": gemm_bytes / gemm_launches,
+                "avg_launch_us": gemm_ms * 1e3 / gemm_launches, "traffic": None,
+                "per_class": {k: {"launches_per_round": cls_n[k] / reps,
+                                  "ms_per_round": cls_ms[k] / reps,
+                                  "gbs": (wb[k] * cls_n[k] / (cls_ms[k] * 1e-3) / 1e9) if k in wb and cls_ms[k] > 0 else None}
+                              for k in eng.KERNEL_CLASSES},
+                "whole_path": {"achieved": bytes_total / (dev_ms_total * 1e-3) / 1e9,
+                               "frac": bytes_total / (dev_ms_total * 1e-3) / 1e9 / peak,
+                               "note": "algorithmic bytes of every round (weights + KV, SURVEY.md 8(d)) / device time of the timed region"}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sd = model.state_dict(dtype=torch.bfloat16, device="cpu")
+            w, w_dtype = cpu_weights(sd, arch)
+            del sd
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            n_cpu, _probe = cpu_sized_sample(args, w, arch, prompts, 20.0)
+            toks, secs, _acc = cpu_reference_run(args, w, arch, prompts, 1, n_cpu)
+            cpu_baseline = {"value": toks / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                            "cpu": cpu_model_name(),
+                            "sample": f"1 generation x {n_cpu} tokens, prompt {args.prompt_len} ids "
+                                      f"(prefill included), oracle port in torch {w_dtype} on {cores} threads; "
+                                      f"{time.perf_counter() - t0:.1f} s of CPU work incl. sizing probe"}
+            del w
+        except Exception as exc:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"failed: {exc!r}"}
+
+    if rank == 0 and not args.no_extra and world == 1:
+        # informative legs: autoregressive on the same engine
+        try:
+            eng.begin(exit_layer=-1, max_steps=args.max_steps, eos_token_ids=eos)
+            eng.prefill(prompts[0])
+            ms, nb = eng.last_device_ms, 0.0
+            for _ in range(128):
+                ctx = eng.kv_len
+                eng.ar_step()
+                ms += eng.last_device_ms
+                nb += eng.ar_bytes(ctx)
+            extra["autoregressive_same_engine"] = {"tokens_per_s": 128 / (ms * 1e-3),
+                                                   "hbm_gbs": nb / (ms * 1e-3) / 1e9}
+        except Exception as exc:  # pragma: no cover
+            extra["autoregressive_same_engine"] = {"error": repr(exc)}
+
+    if rank == 0:
+        acc_mean = sum(accs) / max(1, len(accs))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev * 1e3 / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "acceptance_rate": acc_mean,
+            "config": {"workload": f"{args.arch} arch, random-init (alpha={args.alpha}), "
+                                   f"exit_layer={args.exit_layer}, num_speculations={args.num_speculations}, "
+                                   f"greedy, {args.prompt_len}-id synthetic prompts, {args.max_steps}-token continuations",
+                       "parallelism": f"tp{tp}" if tp > 1 else f"replicas{world}",
+                       "l2": "inputs_exceed_l2 (weights 13.5 GB >> 126 MB L2)",
+                       "step": "one full generation (prefill + rounds)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * args.prompt_len,
+                    "d2h_bytes_per_step": int(rounds_total / max(1, args.steps)) * 212},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu_baseline, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    strat.engines.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,6 +162,14 @@ int lsk_ar_bytes(const lsk_engine* e, int32_t ctx, double* bytes_out);
 int lsk_launch_count(const lsk_engine* e, int64_t* count_out);
 int lsk_last_device_ms(const lsk_engine* e, float* ms_out);
 
+/* Same work as lsk_round, launched eagerly with a CUDA-event pair around every kernel so the
+ * device time can be attributed per kernel class: 0 qkv, 1 attention, 2 o-proj, 3 gate/up,
+ * 4 down, 5 lm-head, 6 small kernels, 7 collectives.  class_ms / class_launches have 8 entries.
+ * Measurement aid for bench.py's roofline section; the numbers include launch gaps that graph
+ * replay + programmatic dependent launch hide in lsk_round. */
+int lsk_profile_round(lsk_engine* e, int32_t d_req, lsk_round_out* out, float* class_ms,
+                      int64_t* class_launches, float* total_ms);
+
 /* Stand-alone kernel entry points used by the micro-benchmarks and unit tests: run the skinny
  * GEMM (y[m, n] = x[m, k] . W[n, k]^T, fp32 out) on packed weights / the split-KV attention on
  * caller-provided device buffers. */

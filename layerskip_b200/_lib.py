@@ -82,6 +82,9 @@ SIGNATURES = {
     "lsk_ar_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "lsk_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "lsk_last_device_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "lsk_profile_round": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(lsk_round_out),
+                                    C.POINTER(C.c_float), C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_float)]),
     "lsk_test_pack": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "lsk_test_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),

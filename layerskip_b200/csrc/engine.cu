@@ -84,6 +84,7 @@ struct lsk_engine {
   int heads_l = 0, kv_heads_l = 0, q_rows = 0, kv_rows = 0, inter_l = 0, vocab_l = 0,
       vocab_l_pad = 0, vocab_off = 0, group = 0;
   int n_pages = 0, max_pos = 0, n_splits = 0;
+  int max_rows = kMaxRows;             // token rows one step can carry (8 when 16 do not fit)
   bool use_pdl = true, use_graph = true, keep_logits = false;
 
   std::vector<LayerWeights> layers;
@@ -121,6 +122,7 @@ struct lsk_engine {
   RoundResult* res_dev = nullptr;      // device alias of res_host
 
   GemmPlan p_qkv, p_o, p_gu, p_d, p_lm;
+  size_t l2_prefetch_bytes = 24u << 20;   // head of the NEXT kernel's weights pulled into L2
   int lm_cand = 0;                     // candidates produced by the LM head (its grid)
 
   cudaStream_t stream = nullptr;
@@ -136,7 +138,13 @@ struct lsk_engine {
   int64_t capture_launches = 0;        // launches recorded while capturing the current graph
   std::map<long long, int64_t> graph_launches;
   float last_ms = 0.f;
+  // per-kernel-class timing (lsk_profile_round): events around every launch, eager mode
+  bool profiling = false;
+  int cur_class = 0;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
 };
+
+enum { CLS_QKV = 0, CLS_ATTN = 1, CLS_O = 2, CLS_GATEUP = 3, CLS_DOWN = 4, CLS_LMHEAD = 5, CLS_MISC = 6, CLS_COMM = 7, CLS_COUNT = 8 };
 
 static constexpr int kSmemMax = 227 * 1024;
 
@@ -158,7 +166,15 @@ static cudaError_t launch(lsk_engine* e, void (*kern)(KArgs...), dim3 grid, dim3
   cfg.numAttrs = e->use_pdl ? 1 : 0;
   e->launches += 1;
   e->capture_launches += 1;
-  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  if (!e->profiling) return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, e->stream);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  cudaEventRecord(b, e->stream);
+  e->prof_events.push_back({e->cur_class, {a, b}});
+  return err;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,32 +185,42 @@ static GemmPlan make_plan(int n_rows, int K, int sm_count) {
   p.n_tiles = n_rows / 16;
   p.K = K;
   p.nsb = K / 32;
-  // K-split across the 16 warps of a CTA: largest power of two that divides nsb and leaves each
-  // warp >= 8 super-blocks (one full prefetch window) to stream.
-  int ks_log2 = 0;
-  while (ks_log2 < 4 && (p.nsb % (2 << ks_log2)) == 0 && p.nsb / (2 << ks_log2) >= 8) ++ks_log2;
-  if (const char* env = getenv("LSK_FORCE_KS_LOG2")) {
-    int f = atoi(env);
-    if (f >= 0 && f <= 4 && p.nsb % (1 << f) == 0) ks_log2 = f;
-  }
-  p.ks_log2 = ks_log2;
-  const int tpc = kGemmWarps >> ks_log2;
-  const int n_groups = (p.n_tiles + tpc - 1) / tpc;
-  // persistent grid: the CTA count <= SMs that wastes the fewest group slots (HBM-bound, so an
-  // exact divisor on fewer SMs beats a ragged last wave on all of them); ties -> more CTAs.
-  int best_g = 1;
-  long best_cost = -1;
-  const int lo = sm_count / 2 > 0 ? sm_count / 2 : 1;
-  for (int g = lo; g <= sm_count; ++g) {
-    const long cost = (long)((n_groups + g - 1) / g) * g;
-    if (best_cost < 0 || cost < best_cost || (cost == best_cost && g > best_g)) {
-      best_cost = cost;
-      best_g = g;
-    }
-  }
-  p.grid = n_groups < lo ? n_groups : best_g;
-  if (p.grid > n_groups) p.grid = n_groups;
+  p.grid = sm_count;      // upper bound; the schedule below trims it to the slot count
   return p;
+}
+
+// Per-launch schedule: how much of K is resident (activation chunk), how many tiles are
+// accumulated side by side, and how deep the TMA ring can be in the remaining shared memory.
+struct GemmSched {
+  int tpp = 1, n_chunks = 1, kc_sbs = 0, n_stages = 0, grid = 0;
+  size_t smem = 0;
+  bool ok = false;
+};
+static GemmSched plan_sched(int NT, int pro, int epi, const GemmPlan& p, int sm_count) {
+  GemmSched best;
+  for (int want = 1; want <= 16; ++want) {
+    if (pro == PRO_RMS && want > 1) break;          // RMSNorm needs the whole row resident
+    int kc = (p.nsb + want - 1) / want;
+    if (want > 1) kc = (kc + kStageSbs - 1) / kStageSbs * kStageSbs;
+    const int n_chunks = (p.nsb + kc - 1) / kc;
+    const int tpp = n_chunks > 1 ? kMaxTilesPerPass : 1;
+    for (int st = kMaxStages; st >= 2; --st) {
+      const GemmSmem L = gemm_smem_layout(NT, kc * 32, tpp, st, epi);
+      if (L.total <= (size_t)kSmemMax) {
+        if (!best.ok || st > best.n_stages) {
+          best.ok = true; best.tpp = tpp; best.n_chunks = n_chunks; best.kc_sbs = kc;
+          best.n_stages = st; best.smem = L.total;
+        }
+        break;
+      }
+    }
+    if (best.ok && best.n_stages >= 5) break;       // >= 80 KiB in flight per SM: enough
+  }
+  if (best.ok) {
+    const int n_slots = (p.n_tiles + best.tpp - 1) / best.tpp;
+    best.grid = n_slots < sm_count ? n_slots : sm_count;
+  }
+  return best;
 }
 
 template <int NT, int PRO, int EPI>
@@ -205,48 +231,45 @@ static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
-  const size_t smem = gemm_smem_bytes<NT>(p.K, EPI, p.ks_log2);
-  if (smem > (size_t)kSmemMax)
-    return fail(LSK_ERR_INVALID, "skinny GEMM needs %zu B shared memory (K=%d, NT=%d)", smem, p.K, NT);
+  const GemmSched sc = plan_sched(NT, PRO, EPI, p, e->sm_count);
+  if (!sc.ok)
+    return fail(LSK_ERR_INVALID, "skinny GEMM does not fit shared memory (K=%d, NT=%d)", p.K, NT);
   a.n_tiles = p.n_tiles;
   a.nsb = p.nsb;
   a.K = p.K;
-  a.ks_log2 = p.ks_log2;
-  CU(launch(e, kern, dim3(p.grid), dim3(kGemmThreads), smem, a));
+  a.tiles_per_pass = sc.tpp;
+  a.n_chunks = sc.n_chunks;
+  a.kc_sbs = sc.kc_sbs;
+  a.n_stages = sc.n_stages;
+  CU(launch(e, kern, dim3(sc.grid), dim3(kGemmThreads), sc.smem, a));
   return LSK_OK;
 }
 
 template <int PRO, int EPI>
 static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
   if (a.M <= 8) return launch_gemm_t<1, PRO, EPI>(e, p, a);
-  if (gemm_smem_bytes<2>(p.K, EPI, p.ks_log2) <= (size_t)kSmemMax)
-    return launch_gemm_t<2, PRO, EPI>(e, p, a);
-  // 16 rows do not fit next to this K: two 8-row passes (only RESID/STORE shapes get here)
-  GemmArgs lo = a, hi = a;
-  lo.M = 8;
-  hi.M = a.M - 8;
-  hi.x_bf16 = a.x_bf16 ? a.x_bf16 + (size_t)8 * a.xb_ld : nullptr;
-  hi.x_f32 = a.x_f32 ? a.x_f32 + (size_t)8 * a.x_ld : nullptr;
-  hi.out_f32 = a.out_f32 ? a.out_f32 + (size_t)8 * a.out_ld : nullptr;
-  if (EPI != EPI_RESID && EPI != EPI_STORE)
-    return fail(LSK_ERR_INVALID, "row-split fallback only supports RESID/STORE epilogues");
-  TRY((launch_gemm_t<1, PRO, EPI>(e, p, lo)));
-  return launch_gemm_t<1, PRO, EPI>(e, p, hi);
+  if (plan_sched(2, PRO, EPI, p, e->sm_count).ok) return launch_gemm_t<2, PRO, EPI>(e, p, a);
+  return fail(LSK_ERR_INVALID, "%d token rows need the 16-row kernel, which does not fit next to K=%d "
+              "(hidden sizes > 4096 support at most 8 rows, i.e. num_speculations <= 7)", a.M, p.K);
 }
 
 // ---------------------------------------------------------------------------------------------
 // one decoder layer on hidden rows [row0, row0 + M) at positions *base_len + pos_off + i
 //   (HF LlamaDecoderLayer as called at llama_model_utils.py:193-201,253-261,354-362,375-383)
 // ---------------------------------------------------------------------------------------------
-static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base_len, int pos_off) {
+static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base_len, int pos_off,
+                         const void* after_W = nullptr, size_t after_bytes = 0) {
   const lsk_config& c = e->cfg;
   LayerWeights& L = e->layers[li];
   float* x = e->hidden + (size_t)row0 * c.hidden;
   __nv_bfloat16* kp = e->kpool + (size_t)li * e->pool_layer_elems;
   __nv_bfloat16* vp = e->vpool + (size_t)li * e->pool_layer_elems;
   const bool tp = c.tp_size > 1;
+  const size_t h2 = (size_t)c.hidden * 2;
+  auto cap = [&](size_t bytes) { return bytes < e->l2_prefetch_bytes ? bytes : e->l2_prefetch_bytes; };
 
   {  // RMSNorm -> QKV -> RoPE -> KV append
+    e->cur_class = CLS_QKV;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wqkv);
     a.M = M;
@@ -255,9 +278,11 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
     a.base_len = base_len; a.pos_off = pos_off; a.rope = e->rope;
     a.q_rows = e->q_rows; a.kv_rows = e->kv_rows; a.n_kv_heads = e->kv_heads_l;
+    a.next_W = L.wo; a.next_bytes = e->l2_prefetch_bytes ? (size_t)e->q_rows * h2 : 0;
     TRY((launch_gemm<PRO_RMS, EPI_QKV>(e, e->p_qkv, a)));
   }
   {  // attention over the paged cache
+    e->cur_class = CLS_ATTN;
     AttnArgs a{};
     a.q = e->qbuf; a.q_ld = e->q_rows; a.out = e->attn_out; a.out_ld = e->q_rows;
     a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
@@ -269,10 +294,12 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     CU(launch(e, attn_splitkv_kernel, dim3(e->kv_heads_l, e->n_splits), dim3(kAttnThreads), 0, a));
   }
   {  // O projection (+ residual, or all-reduce then residual under TP)
+    e->cur_class = CLS_O;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wo);
     a.M = M;
     a.x_bf16 = e->attn_out; a.xb_ld = e->q_rows;
+    a.next_W = L.wgu; a.next_bytes = cap((size_t)2 * e->inter_l * h2);
     if (!tp) {
       a.out_f32 = x; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_RESID>(e, e->p_o, a)));
@@ -280,22 +307,27 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_o, a)));
       NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+      e->cur_class = CLS_MISC;
       CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
     }
   }
   {  // RMSNorm -> gate/up -> SiLU * up
+    e->cur_class = CLS_GATEUP;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wgu);
     a.M = M;
     a.x_f32 = x; a.x_ld = c.hidden; a.norm_w = L.ln2; a.eps = c.rms_eps;
     a.act = e->act; a.act_ld = e->inter_l;
+    a.next_W = L.wd; a.next_bytes = cap((size_t)e->inter_l * h2);
     TRY((launch_gemm<PRO_RMS, EPI_SILU>(e, e->p_gu, a)));
   }
   {  // down projection (+ residual)
+    e->cur_class = CLS_DOWN;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wd);
     a.M = M;
     a.x_bf16 = e->act; a.xb_ld = e->inter_l;
+    a.next_W = after_W; a.next_bytes = after_W ? cap(after_bytes) : 0;
     if (!tp) {
       a.out_f32 = x; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_RESID>(e, e->p_d, a)));
@@ -303,6 +335,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_d, a)));
       NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+      e->cur_class = CLS_MISC;
       CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
     }
   }
@@ -312,8 +345,9 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
 // final RMSNorm + LM head on rows [row0, row0+M): arg-max candidates (and optional logits).
 // (llama_model_utils.py:204-205, 271-273, 386-387).  Afterwards e->cand_* / n_cand() hold one
 // (value, index) per candidate per row.
-static int enqueue_lm_head(lsk_engine* e, int row0, int M) {
+static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W = nullptr, size_t after_bytes = 0) {
   const lsk_config& c = e->cfg;
+  e->cur_class = CLS_LMHEAD;
   GemmArgs a{};
   a.W = reinterpret_cast<const uint4*>(e->lm_head);
   a.M = M;
@@ -322,7 +356,10 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M) {
   a.logits = e->keep_logits ? e->logits : nullptr; a.logits_ld = e->vocab_l_pad;
   a.n_valid_rows = e->vocab_l; a.vocab_off = e->vocab_off;
   a.part_val = e->cand_val; a.part_idx = e->cand_idx;
+  a.next_W = after_W;
+  a.next_bytes = after_W ? (after_bytes < e->l2_prefetch_bytes ? after_bytes : e->l2_prefetch_bytes) : 0;
   TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
+  e->cur_class = CLS_MISC;
   if (c.tp_size > 1) {
     CU(launch(e, rank_best_kernel, dim3(1), dim3(256), 0, (const float*)e->cand_val,
               (const int*)e->cand_idx, e->lm_cand, M, e->rank_val, e->rank_idx));
@@ -342,23 +379,37 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   const lsk_config& c = e->cfg;
   const int* len = &e->state->len;
   // row 0 <- embedding of the pending token (self_speculation_generator.py:122, input_ids)
+  e->cur_class = CLS_MISC;
   CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
             (const int*)&e->state->tok[0], e->hidden, c.hidden));
   // draft loop (:127-148): step i runs layers [0,E) on row i at position len+i, then the shared
   // head; its arg-max becomes tok[i+1] and is embedded into row i+1.
+  const size_t qkv_bytes = (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2;
+  const size_t lm_bytes = (size_t)e->vocab_l_pad * c.hidden * 2;
+  auto layer_then = [&](int l, int row0, int M, int pos_off, int stop) -> int {
+    // what streams after layer l: the next layer's QKV, or the LM head at the end of a pass
+    const void* nw = (l + 1 < stop) ? (const void*)e->layers[l + 1].wqkv : (const void*)e->lm_head;
+    const size_t nb = (l + 1 < stop) ? qkv_bytes : lm_bytes;
+    return enqueue_layer(e, l, row0, M, len, pos_off, nw, nb);
+  };
   for (int i = 0; i < d; ++i) {
-    for (int l = 0; l < E; ++l) TRY(enqueue_layer(e, l, i, 1, len, i));
-    TRY(enqueue_lm_head(e, i, 1));
+    for (int l = 0; l < E; ++l) TRY(layer_then(l, i, 1, i, E));
+    TRY(enqueue_lm_head(e, i, 1, e->layers[0].wqkv, qkv_bytes));
+    e->cur_class = CLS_MISC;
     CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
               e->state, 1 + i, (const __nv_bfloat16*)e->embed, c.hidden,
               e->hidden + (size_t)(i + 1) * c.hidden));
   }
   // verify (:164-174 -> llama_model_utils.py:280-391): the last drafted token has not been
   // through layers < E yet (:350-362) ...
-  for (int l = 0; l < E; ++l) TRY(enqueue_layer(e, l, d, 1, len, d));
+  for (int l = 0; l < E; ++l) {
+    if (l + 1 < E || E < c.n_layers) TRY(enqueue_layer(e, l, d, 1, len, d, e->layers[l + 1].wqkv, qkv_bytes));
+    else TRY(enqueue_layer(e, l, d, 1, len, d, e->lm_head, lm_bytes));
+  }
   // ... then layers >= E see [exit rows of the draft steps ; that row] = rows 0..d (:363-383)
-  for (int l = E; l < c.n_layers; ++l) TRY(enqueue_layer(e, l, 0, d + 1, len, 0));
-  TRY(enqueue_lm_head(e, 0, d + 1));
+  for (int l = E; l < c.n_layers; ++l) TRY(layer_then(l, 0, d + 1, 0, c.n_layers));
+  TRY(enqueue_lm_head(e, 0, d + 1, e->layers[0].wqkv, qkv_bytes));
+  e->cur_class = CLS_MISC;
   CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d,
             e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
   return LSK_OK;
@@ -369,8 +420,13 @@ static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
   const int* len = &e->state->len;
   CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
             (const int*)&e->state->tok[0], e->hidden, c.hidden));
-  for (int l = 0; l < n_layers_run; ++l) TRY(enqueue_layer(e, l, 0, 1, len, 0));
-  TRY(enqueue_lm_head(e, 0, 1));
+  const size_t qkv_bytes = (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2;
+  const size_t lm_bytes = (size_t)e->vocab_l_pad * c.hidden * 2;
+  for (int l = 0; l < n_layers_run; ++l) {
+    if (l + 1 < n_layers_run) TRY(enqueue_layer(e, l, 0, 1, len, 0, e->layers[l + 1].wqkv, qkv_bytes));
+    else TRY(enqueue_layer(e, l, 0, 1, len, 0, e->lm_head, lm_bytes));
+  }
+  TRY(enqueue_lm_head(e, 0, 1, e->layers[0].wqkv, qkv_bytes));
   CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
             e->res_dev, seq));
   return LSK_OK;
@@ -458,9 +514,9 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   e->p_gu = make_plan(2 * e->inter_l, c.hidden, e->sm_count);
   e->p_d = make_plan(c.hidden, e->inter_l, e->sm_count);
   e->p_lm = make_plan(e->vocab_l_pad, c.hidden, e->sm_count);
-  e->lm_cand = e->p_lm.grid;
-  if (gemm_smem_bytes<1>(e->inter_l, EPI_RESID, e->p_d.ks_log2) > (size_t)kSmemMax)
-    return fail(LSK_ERR_INVALID, "intermediate size per rank (%d) too large for the resident-activation down projection", e->inter_l);
+  e->lm_cand = e->p_lm.n_tiles < e->sm_count ? e->p_lm.n_tiles : e->sm_count;
+  if (const char* env = getenv("LSK_L2_PREFETCH_MB")) e->l2_prefetch_bytes = (size_t)atoi(env) << 20;
+  e->max_rows = plan_sched(2, PRO_RMS, EPI_QKV, e->p_qkv, e->sm_count).ok ? kMaxRows : 8;
 
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&e->ev0));
@@ -703,11 +759,13 @@ int lsk_prefill(lsk_engine* e, const int32_t* ids, int32_t n) {
   CU(cudaMemcpyAsync(e->d_prompt, ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
   // ids[0 .. n-2] through every layer in blocks of <= 16 rows; no LM head: the reference
   // discards those logits too (self_speculation_generator.py:177).
-  for (int c0 = 0; c0 < n - 1; c0 += kMaxRows) {
-    const int m = (n - 1 - c0) < kMaxRows ? (n - 1 - c0) : kMaxRows;
+  for (int c0 = 0; c0 < n - 1; c0 += e->max_rows) {
+    const int m = (n - 1 - c0) < e->max_rows ? (n - 1 - c0) : e->max_rows;
     CU(launch(e, embed_tokens_kernel, dim3(m), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
               (const int*)(e->d_prompt + c0), e->hidden, c.hidden));
-    for (int l = 0; l < c.n_layers; ++l) TRY(enqueue_layer(e, l, 0, m, e->d_zero, c0));
+    for (int l = 0; l < c.n_layers; ++l)
+      TRY(enqueue_layer(e, l, 0, m, e->d_zero, c0, e->layers[(l + 1) % c.n_layers].wqkv,
+                        (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2));
   }
   set_state_kernel<<<1, 1, 0, e->stream>>>(e->state, n - 1, ids[n - 1], 0);
   CU(cudaGetLastError());
@@ -735,7 +793,7 @@ static void copy_result(const lsk_engine* e, lsk_round_out* out) {
 int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
   if (!e || !out) return fail(LSK_ERR_INVALID, "null argument");
   if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_round");
-  if (d_req < 0 || d_req > LSK_MAX_SPEC) return fail(LSK_ERR_INVALID, "d_req %d out of [0,%d]", d_req, LSK_MAX_SPEC);
+  if (d_req < 0 || d_req + 1 > e->max_rows) return fail(LSK_ERR_INVALID, "d_req %d out of [0,%d]", d_req, e->max_rows - 1);
   const int E = e->gen.exit_layer;
   if (E < 1 || E > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "self-speculation needs 1 <= exit_layer <= n_layers (got %d)", E);
   if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context %d + %d exceeds max_ctx", e->host_len, d_req + 1);
@@ -757,6 +815,39 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
   TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
   *token_out = e->res_host->emitted_ids[0];
   e->host_len = e->res_host->kv_len;
+  return LSK_OK;
+}
+
+int lsk_profile_round(lsk_engine* e, int32_t d_req, lsk_round_out* out, float* class_ms,
+                      int64_t* class_launches, float* total_ms) {
+  if (!e || !out || !class_ms || !class_launches) return fail(LSK_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_profile_round");
+  if (d_req < 0 || d_req > LSK_MAX_SPEC) return fail(LSK_ERR_INVALID, "d_req out of range");
+  const int E = e->gen.exit_layer;
+  if (E < 1 || E > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "bad exit_layer");
+  if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
+  e->profiling = true;
+  e->prof_events.clear();
+  CU(cudaEventRecord(e->ev0, e->stream));
+  int st = enqueue_round(e, E, d_req, 0);
+  e->profiling = false;
+  if (st != LSK_OK) return st;
+  CU(cudaEventRecord(e->ev1, e->stream));
+  CU(cudaEventSynchronize(e->ev1));
+  CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  if (total_ms) *total_ms = e->last_ms;
+  for (int i = 0; i < CLS_COUNT; ++i) { class_ms[i] = 0.f; class_launches[i] = 0; }
+  for (auto& pe : e->prof_events) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
+    class_ms[pe.first] += ms;
+    class_launches[pe.first] += 1;
+    cudaEventDestroy(pe.second.first);
+    cudaEventDestroy(pe.second.second);
+  }
+  e->prof_events.clear();
+  copy_result(e, out);
+  e->host_len = out->kv_len;
   return LSK_OK;
 }
 

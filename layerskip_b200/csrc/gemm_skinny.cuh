@@ -1,8 +1,11 @@
 // gemm_skinny.cuh — weight-streaming "skinny" GEMM for decode shapes:
 //     y[m, n] = sum_k x[m, k] * W[n, k]        m <= 16 tokens,  W bf16 [N, K] (HF layout)
-// HBM-bound by construction (arithmetic intensity <= 16 flop/B): the kernel is a stream of
-// fully coalesced 128-bit loads of PRE-SHUFFLED weights straight into mma.sync A-fragments,
-// with the (tiny) activation block resident in shared memory as the B operand.
+// HBM-bound by construction (arithmetic intensity <= 16 flop/B).  PRE-SHUFFLED weights are
+// streamed by the TMA engine (1-D cp.async.bulk, global -> shared, mbarrier completion) through
+// a multi-stage shared-memory ring: ~100 KB per SM in flight with no L1 miss tracking involved
+// (measured: the LDG path saturates near 45 GB/s per SM, far below HBM / 148).  Consumer warps
+// lift mma.sync A-fragments out of the ring with conflict-free 128-bit shared loads; the (tiny)
+// activation block is resident in shared memory as the B operand.
 //
 // Packed weight layout (built once by pack_rows_kernel, see engine.cu):
 //   tile   = 16 consecutive output rows,  super-block (sb) = 32 consecutive k
@@ -24,17 +27,76 @@ namespace lsk {
 enum { PRO_RMS = 0, PRO_BF16 = 1 };
 enum { EPI_QKV = 0, EPI_RESID = 1, EPI_STORE = 2, EPI_SILU = 3, EPI_LMHEAD = 4 };
 
-constexpr int kGemmWarps = 16;
-constexpr int kGemmThreads = kGemmWarps * 32;
-constexpr int kPrefetch = 8;  // super-blocks in flight per warp (16 x 16 B per lane)
+constexpr int kGemmWarps = 16;                       // consumer warps (LDS + MMA)
+constexpr int kEpiWarps = 3;                         // reduction / epilogue warps
+constexpr int kConsumerThreads = kGemmWarps * 32;    // 512
+constexpr int kEpiThreads = kEpiWarps * 32;          // 96
+constexpr int kGemmThreads = kConsumerThreads + 32 + kEpiThreads;   // + 1 producer warp = 640
+constexpr int kWorkThreads = kConsumerThreads + kEpiThreads;        // everyone but the producer
+constexpr int kProducerWarp = kGemmWarps;            // warp 16
+constexpr int kStageSbs = 16;                        // super-blocks (1 KiB each) per ring stage
+constexpr int kStageBytes = kStageSbs * 1024;
+constexpr int kMaxStages = 8;
+constexpr int kMaxTilesPerPass = 2;
+
+// named barriers (0 is __syncthreads)
+enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4, BAR_EPI = 5, BAR_CONS = 6,
+       BAR_WORK = 7 };
+__device__ __forceinline__ void bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+// fire-and-forget: pull [p, p+bytes) into L2 (bytes % 16 == 0)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// ---- mbarrier + TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct GemmArgs {
   const uint4* W;       // packed weights
   int n_tiles;          // N / 16
   int nsb;              // K / 32
   int K;
-  int ks_log2;          // log2 of the K-split across the warps of a CTA
   int M;                // valid token rows
+  // ---- schedule (host-planned, see plan_gemm in engine.cu)
+  int tiles_per_pass;   // 1 or 2 tiles accumulated side by side (needed when K is chunked)
+  int n_chunks;         // K chunks whose activations are resident at a time
+  int kc_sbs;           // super-blocks per chunk (multiple of kStageSbs unless n_chunks == 1)
+  int n_stages;         // ring depth
+  // ---- next kernel's weights: its head is pulled into L2 while this kernel drains
+  const void* next_W;
+  unsigned long long next_bytes;   // bytes worth prefetching (0 = none)
   // ---- prologue
   const float* x_f32;   // PRO_RMS: residual-stream rows [M][x_ld] fp32
   int x_ld;
@@ -69,93 +131,154 @@ struct GemmArgs {
   int* part_idx;
 };
 
-__host__ __device__ inline int gemm_x_stride_bytes(int K) {
-  return ((2 * K + 127) / 128) * 128 + 64;   // == 64 (mod 128): conflict-free LDS.128
+__host__ __device__ inline int gemm_x_stride_bytes(int kcols) {
+  return ((2 * kcols + 127) / 128) * 128 + 64;   // == 64 (mod 128): conflict-free LDS.128
 }
 
-template <int NT>
-__host__ __device__ inline size_t gemm_smem_bytes(int K, int epi, int ks_log2) {
-  size_t s = (size_t)NT * 8 * gemm_x_stride_bytes(K);     // activations
-  s += (size_t)kGemmWarps * NT * 128 * 4;                 // cross-warp reduction
-  s += (size_t)(kGemmWarps + 1) * NT * 8 * 4;             // rms partials + rstd
-  if (epi == EPI_LMHEAD) s += (size_t)NT * 8 * ((kGemmWarps >> ks_log2) * 16) * 4;
-  return s;
+// shared-memory carve-up (host and device must agree)
+struct GemmSmem {
+  size_t ring, xs, red, stat, lg, bars, total;
+};
+__host__ __device__ inline GemmSmem gemm_smem_layout(int NT, int kc_cols, int tpp, int n_stages, int epi) {
+  GemmSmem L;
+  size_t off = 0;
+  L.ring = off; off += (size_t)n_stages * kStageBytes;
+  L.xs = off;   off += (size_t)NT * 8 * gemm_x_stride_bytes(kc_cols);
+  L.red = off;  off += (size_t)2 * tpp * kGemmWarps * NT * 128 * 4;
+  L.stat = off; off += (size_t)(kGemmWarps + kEpiWarps + 1) * NT * 8 * 4;
+  L.lg = off;   if (epi == EPI_LMHEAD) off += (size_t)NT * 8 * (tpp * 16) * 4;
+  off = (off + 15) & ~(size_t)15;
+  L.bars = off; off += (size_t)2 * kMaxStages * 8;
+  L.total = off;
+  return L;
 }
 
+// Kernel structure (one CTA per SM, persistent over tiles; 20 warps):
+//   warp 16      : PRODUCER — one elected lane walks this CTA's weight byte stream (tile after
+//                  tile, 16 KiB stages) and issues TMA bulk copies into the ring as slots free
+//                  up; it starts before the previous kernel has finished (weights never depend
+//                  on it) so the ring is full when the activations arrive
+//   warps 0..15  : CONSUMERS — warp w owns super-block w of every stage (an interleaved 16-way
+//                  K split): A fragments from the ring, B fragments from the resident
+//                  activations, mma.sync into per-tile accumulators; partial tiles are handed
+//                  to the epilogue warps through a double-buffered slot
+//   warps 17..19 : EPILOGUE — fixed-order reduction over the 16 K-slices + fused epilogue,
+//                  overlapped with the streaming of the next tile; at the end they pull the
+//                  NEXT kernel's first weights into L2.
 template <int NT, int PRO, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_skinny_kernel(const GemmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int XS = gemm_x_stride_bytes(a.K);
-  unsigned char* xs = smem;
-  float* red = reinterpret_cast<float*>(smem + (size_t)NT * 8 * XS);
-  float* stat = red + kGemmWarps * NT * 128;
-  float* lg = stat + (kGemmWarps + 1) * NT * 8;
+  const int TPP = a.tiles_per_pass;
+  const int kc_cols = a.kc_sbs * 32;
+  const GemmSmem L = gemm_smem_layout(NT, kc_cols, TPP, a.n_stages, EPI);
+  const int XS = gemm_x_stride_bytes(kc_cols);
+  unsigned char* ring = smem + L.ring;
+  unsigned char* xs = smem + L.xs;
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  const int kRedFloats = TPP * kGemmWarps * NT * 128;     // one buffer
+  float* stat = reinterpret_cast<float*>(smem + L.stat);
+  constexpr int kStatWarps = kGemmWarps + kEpiWarps;
+  float* lg = reinterpret_cast<float*>(smem + L.lg);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* empty_bar = full_bar + kMaxStages;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int KS = 1 << a.ks_log2;
-  const int TPC = kGemmWarps >> a.ks_log2;
-  const int tile_local = warp >> a.ks_log2;
-  const int ks = warp & (KS - 1);
-  const int sb_per = a.nsb >> a.ks_log2;
-  const int sb0 = ks * sb_per;
-  const int n_groups = (a.n_tiles + TPC - 1) / TPC;
+  const int n_slots = (a.n_tiles + TPP - 1) / TPP;        // a slot = TPP adjacent tiles
+  const int NS = a.n_stages;
 
-  uint4 abuf[kPrefetch][2];
-  auto prefetch_head = [&](int grp) {
-    const int tile = grp * TPC + tile_local;
-    if (grp < n_groups && tile < a.n_tiles) {
-      const uint4* wp = a.W + ((size_t)tile * a.nsb + sb0) * 64 + lane;
-#pragma unroll
-      for (int i = 0; i < kPrefetch; ++i)
-        if (i < sb_per) {
-          abuf[i][0] = ldg_stream(wp + i * 64);
-          abuf[i][1] = ldg_stream(wp + i * 64 + 32);
-        }
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kGemmWarps);
     }
-  };
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
-  // Weights never depend on the previous kernel: get the stream going before the dependency.
-  prefetch_head(blockIdx.x);
+  if (warp == kProducerWarp) {
+    // ================================================================== PRODUCER
+    pdl_launch_dependents();
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        for (int kc = 0; kc < a.n_chunks; ++kc) {
+          const int sb_lo = kc * a.kc_sbs;
+          const int sb_hi = min(a.nsb, sb_lo + a.kc_sbs);
+          for (int j = 0; j < TPP; ++j) {
+            const int tile = slot * TPP + j;
+            if (tile >= a.n_tiles) break;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.W) +
+                                       ((size_t)tile * a.nsb + sb_lo) * 1024;
+            for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
+              const int cnt = min(kStageSbs, sb_hi - sb);
+              const int s = q % NS;
+              mbar_wait(&empty_bar[s], ((q / NS) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cnt * 1024);
+              tma_bulk_g2s(ring + (size_t)s * kStageBytes, src + (size_t)(sb - sb_lo) * 1024,
+                           (uint32_t)cnt * 1024, &full_bar[s]);
+            }
+          }
+        }
+      }
+    }
+    pdl_wait();   // completion stays transitive along the PDL chain
+    return;
+  }
+
   pdl_launch_dependents();
   pdl_wait();
+  const int wtid = (warp < kGemmWarps) ? tid : tid - 32;   // 0..607 over consumers + epilogue
+
+  // fills the resident activation chunk kc (bf16 source); callers sync around it
+  auto load_x_bf16 = [&](int kc, int ltid, int nthreads) {
+    const int col0 = kc * kc_cols;
+    const int cols = min(a.K - col0, kc_cols);
+    const int nvec = cols >> 3;                // uint4 (8 bf16) per row
+    const int zvec = kc_cols >> 3;
+    for (int m = 0; m < NT * 8; ++m) {
+      for (int idx = ltid; idx < zvec; idx += nthreads) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (m < a.M && idx < nvec)
+          v = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)m * a.xb_ld + col0 + idx * 8);
+        *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = v;
+      }
+    }
+  };
 
   // ------------------------------------------------------------------ prologue: x -> smem
   if (PRO == PRO_RMS) {
     // Two passes over the (L1/L2-resident) residual rows: sum of squares, then normalise ->
-    // bf16 (rounding point of a bf16 HF model: modeling_llama.py:52-70).  Low register use so
-    // the weight prefetch issued above stays in flight.
+    // bf16 (rounding point of a bf16 HF model: modeling_llama.py:52-70).  n_chunks == 1 here.
     const int nvec = a.K >> 2;  // float4 per row
-    float ss[NT * 8];
-#pragma unroll
+    const int swarp = (warp < kGemmWarps) ? warp : warp - 1;
+#pragma unroll 1
     for (int m = 0; m < NT * 8; ++m) {
-      ss[m] = 0.f;
+      float ss = 0.f;
       if (m < a.M) {
         const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)m * a.x_ld);
-        for (int idx = tid; idx < nvec; idx += kGemmThreads) {
+        for (int idx = wtid; idx < nvec; idx += kWorkThreads) {
           const float4 v = xr[idx];
-          ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         }
       }
+      ss = warp_sum(ss);
+      if (lane == 0) stat[swarp * (NT * 8) + m] = ss;
     }
-#pragma unroll
-    for (int m = 0; m < NT * 8; ++m) {
-      const float tot = warp_sum(ss[m]);
-      if (lane == 0) stat[warp * (NT * 8) + m] = tot;
-    }
-    __syncthreads();
-    if (tid < NT * 8) {
+    bar_sync(BAR_WORK, kWorkThreads);
+    if (wtid < NT * 8) {
       float tot = 0.f;
-      for (int w = 0; w < kGemmWarps; ++w) tot += stat[w * (NT * 8) + tid];
-      stat[kGemmWarps * NT * 8 + tid] = rsqrtf(tot / (float)a.K + a.eps);
+      for (int w = 0; w < kStatWarps; ++w) tot += stat[w * (NT * 8) + wtid];
+      stat[kStatWarps * NT * 8 + wtid] = rsqrtf(tot / (float)a.K + a.eps);
     }
-    __syncthreads();
+    bar_sync(BAR_WORK, kWorkThreads);
+#pragma unroll 1
     for (int m = 0; m < NT * 8; ++m) {
       if (m < a.M) {
-        const float rstd = stat[kGemmWarps * NT * 8 + m];
+        const float rstd = stat[kStatWarps * NT * 8 + m];
         const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)m * a.x_ld);
-        for (int idx = tid; idx < nvec; idx += kGemmThreads) {
+        for (int idx = wtid; idx < nvec; idx += kWorkThreads) {
           const float4 v = xr[idx];
           const uint2 wv = *reinterpret_cast<const uint2*>(a.norm_w + idx * 4);
           uint2 o;
@@ -164,166 +287,222 @@ gemm_skinny_kernel(const GemmArgs a) {
           *reinterpret_cast<uint2*>(xs + (size_t)m * XS + idx * 8) = o;
         }
       } else {
-        for (int idx = tid; idx < (a.K >> 3); idx += kGemmThreads)
+        for (int idx = wtid; idx < (kc_cols >> 3); idx += kWorkThreads)
           *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = make_uint4(0, 0, 0, 0);
       }
     }
-    __syncthreads();
+  } else if (a.n_chunks == 1) {
+    load_x_bf16(0, wtid, kWorkThreads);
+  }
+  bar_sync(BAR_WORK, kWorkThreads);
+
+  if (warp < kGemmWarps) {
+    // ================================================================== CONSUMER warps
+    const unsigned char* xlane = xs + (size_t)g * XS + t * 16;
+    uint32_t q = 0;
+    int it = 0;
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
+      float acc[kMaxTilesPerPass][NT][2][4];
+#pragma unroll
+      for (int j = 0; j < kMaxTilesPerPass; ++j)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) acc[j][n][h][0] = acc[j][n][h][1] = acc[j][n][h][2] = acc[j][n][h][3] = 0.f;
+
+      for (int kc = 0; kc < a.n_chunks; ++kc) {
+        if (a.n_chunks > 1) {            // swap the resident activation chunk
+          bar_sync(BAR_CONS, kConsumerThreads);
+          load_x_bf16(kc, tid, kConsumerThreads);
+          bar_sync(BAR_CONS, kConsumerThreads);
+        }
+        const int sb_lo = kc * a.kc_sbs;
+        const int sb_hi = min(a.nsb, sb_lo + a.kc_sbs);
+#pragma unroll
+        for (int j = 0; j < kMaxTilesPerPass; ++j) {
+          if (j < TPP && slot * TPP + j < a.n_tiles) {
+            for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
+              const int s = q % NS;
+              mbar_wait(&full_bar[s], (q / NS) & 1);
+              if (sb + warp < sb_hi) {
+                const unsigned char* ap = ring + (size_t)s * kStageBytes + warp * 1024 + lane * 16;
+                const uint4 a0 = *reinterpret_cast<const uint4*>(ap);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(ap + 512);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                  const uint4 b = *reinterpret_cast<const uint4*>(
+                      xlane + (size_t)n * 8 * XS + (size_t)(sb + warp - sb_lo) * 64);
+                  mma_bf16_16816(acc[j][n][0], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
+                  mma_bf16_16816(acc[j][n][1], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
+                }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+          }
+        }
+      }
+
+      const int buf = it & 1;
+      if (it >= 2) bar_sync(BAR_EMPTY0 + buf, kWorkThreads);   // epilogue released this slot
+      float* rbase = red + buf * kRedFloats;
+#pragma unroll
+      for (int j = 0; j < kMaxTilesPerPass; ++j) {
+        if (j < TPP) {
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            float* r = rbase + (((j * kGemmWarps + warp) * NT + n) * 16) * 8;
+            *reinterpret_cast<float2*>(r + g * 8 + 2 * t) =
+                make_float2(acc[j][n][0][0] + acc[j][n][1][0], acc[j][n][0][1] + acc[j][n][1][1]);
+            *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * t) =
+                make_float2(acc[j][n][0][2] + acc[j][n][1][2], acc[j][n][0][3] + acc[j][n][1][3]);
+          }
+        }
+      }
+      bar_arrive(BAR_FULL0 + buf, kWorkThreads);
+    }
   } else {
-    const int nvec = a.K >> 3;  // uint4 (8 bf16) per row
-    for (int m = 0; m < NT * 8; ++m) {
-      for (int idx = tid; idx < nvec; idx += kGemmThreads) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (m < a.M) v = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)m * a.xb_ld + idx * 8);
-        *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = v;
-      }
-    }
-    __syncthreads();
-  }
-
-  const unsigned char* xlane = xs + (size_t)g * XS + t * 16;
-
-  float best_v = -INFINITY;  // LMHEAD running arg-max (warp `m` owns token m)
-  int best_i = 0x7fffffff;
-
-  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int tile = grp * TPC + tile_local;
-    float acc[NT][4];
+    // ================================================================== EPILOGUE warps
+    const int etid = tid - kConsumerThreads - 32;   // 0..95
+    const int ewarp = warp - kGemmWarps - 1;        // 0..2
+    constexpr int kRowsPerEwarp = (NT * 8 + kEpiWarps - 1) / kEpiWarps;
+    float best_v[kRowsPerEwarp];                    // LMHEAD: running arg-max, rows ewarp + 3*i
+    int best_i[kRowsPerEwarp];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    for (int i = 0; i < kRowsPerEwarp; ++i) { best_v[i] = -INFINITY; best_i[i] = 0x7fffffff; }
 
-    if (tile < a.n_tiles) {
-      const uint4* wp = a.W + ((size_t)tile * a.nsb + sb0) * 64 + lane;
-      for (int sb = 0; sb < sb_per; sb += kPrefetch) {
-#pragma unroll
-        for (int i = 0; i < kPrefetch; ++i) {
-          if (sb + i < sb_per) {
-            const uint4 a0 = abuf[i][0], a1 = abuf[i][1];
-            if (sb + i + kPrefetch < sb_per) {
-              abuf[i][0] = ldg_stream(wp + (size_t)(sb + i + kPrefetch) * 64);
-              abuf[i][1] = ldg_stream(wp + (size_t)(sb + i + kPrefetch) * 64 + 32);
-            }
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-              const uint4 b = *reinterpret_cast<const uint4*>(
-                  xlane + (size_t)n * 8 * XS + (size_t)(sb0 + sb + i) * 64);
-              mma_bf16_16816(acc[n], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
-              mma_bf16_16816(acc[n], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
-            }
+    int it = 0;
+    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const bool last = slot + gridDim.x >= n_slots;
+      if (last && a.next_bytes != 0) {
+        // HBM keeps streaming while this kernel drains and the next one ramps up
+        const unsigned long long share = ((a.next_bytes / gridDim.x) + 15) & ~15ull;
+        const unsigned long long lo = (unsigned long long)blockIdx.x * share;
+        if (lo < a.next_bytes) {
+          unsigned long long len = a.next_bytes - lo < share ? a.next_bytes - lo : share;
+          len &= ~15ull;
+          const unsigned long long per = ((len / kEpiThreads) + 15) & ~15ull;
+          const unsigned long long mylo = (unsigned long long)etid * per;
+          if (mylo < len && per > 0) {
+            const unsigned long long mylen = len - mylo < per ? len - mylo : per;
+            l2_prefetch_bulk(static_cast<const unsigned char*>(a.next_W) + lo + mylo, (uint32_t)mylen);
           }
         }
       }
-    }
-    // keep the HBM stream busy across the reduction / epilogue of this group
-    prefetch_head(grp + gridDim.x);
-
+      bar_sync(BAR_FULL0 + buf, kWorkThreads);
+      const float* rbase = red + buf * kRedFloats;
+      auto ksum = [&](int j, int n, int row, int tok) {
+        float s = 0.f;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      float* r = red + ((warp * NT + n) * 16) * 8;
-      *reinterpret_cast<float2*>(r + g * 8 + 2 * t) = make_float2(acc[n][0], acc[n][1]);
-      *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * t) = make_float2(acc[n][2], acc[n][3]);
-    }
-    __syncthreads();
+        for (int k = 0; k < kGemmWarps; ++k)
+          s += rbase[(((j * kGemmWarps + k) * NT + n) * 16 + row) * 8 + tok];
+        return s;
+      };
 
-    auto ksum = [&](int tl, int n, int row, int tok) {
-      float s = 0.f;
-      for (int k = 0; k < KS; ++k) s += red[((((tl << a.ks_log2) + k) * NT + n) * 16 + row) * 8 + tok];
-      return s;
-    };
-
-    if (EPI == EPI_QKV || EPI == EPI_SILU) {
-      const int items = TPC * NT * 64;
-      for (int it = tid; it < items; it += kGemmThreads) {
-        const int tok = it & 7, r = (it >> 3) & 7, n = (it >> 6) % NT, tl = (it >> 6) / NT;
-        const int m = n * 8 + tok;
-        const int tl_tile = grp * TPC + tl;
-        if (m >= a.M || tl_tile >= a.n_tiles) continue;
-        const float lo = ksum(tl, n, r, tok), hi = ksum(tl, n, r + 8, tok);
-        if (EPI == EPI_SILU) {
-          const float s = lo / (1.f + __expf(-lo));
-          a.act[(size_t)m * a.act_ld + tl_tile * 8 + r] = __float2bfloat16_rn(s * hi);
-        } else {
-          const int pr = tl_tile * 16;                  // first packed row of the tile
-          const int pos = *a.base_len + a.pos_off + m;
-          if (pr < a.q_rows + a.kv_rows) {              // q or k: rotary pair (d, d + 64)
-            const bool is_q = pr < a.q_rows;
-            const int rel = is_q ? pr : pr - a.q_rows;
-            const int head = rel >> 7, tt = (rel & 127) >> 4;
-            const int d = tt * 8 + r;
-            const float2 cs = a.rope[(size_t)pos * 64 + d];
-            const float o_lo = lo * cs.x - hi * cs.y;
-            const float o_hi = hi * cs.x + lo * cs.y;
-            if (is_q) {
-              __nv_bfloat16* q = a.q_out + (size_t)m * a.q_ld + head * 128;
-              q[d] = __float2bfloat16_rn(o_lo);
-              q[d + 64] = __float2bfloat16_rn(o_hi);
-            } else {
+      if (EPI == EPI_QKV || EPI == EPI_SILU) {
+        const int items = TPP * NT * 64;
+        for (int itx = etid; itx < items; itx += kEpiThreads) {
+          const int tok = itx & 7, r = (itx >> 3) & 7, n = (itx >> 6) % NT, j = (itx >> 6) / NT;
+          const int m = n * 8 + tok;
+          const int tile = slot * TPP + j;
+          if (m >= a.M || tile >= a.n_tiles) continue;
+          const float lo = ksum(j, n, r, tok), hi = ksum(j, n, r + 8, tok);
+          if (EPI == EPI_SILU) {
+            const float sg = lo / (1.f + __expf(-lo));
+            a.act[(size_t)m * a.act_ld + tile * 8 + r] = __float2bfloat16_rn(sg * hi);
+          } else {
+            const int pr = tile * 16;                     // first packed row of the tile
+            const int pos = *a.base_len + a.pos_off + m;
+            if (pr < a.q_rows + a.kv_rows) {              // q or k: rotary pair (d, d + 64)
+              const bool is_q = pr < a.q_rows;
+              const int rel = is_q ? pr : pr - a.q_rows;
+              const int head = rel >> 7, tt = (rel & 127) >> 4;
+              const int d = tt * 8 + r;
+              const float2 cs = a.rope[(size_t)pos * 64 + d];
+              const float o_lo = lo * cs.x - hi * cs.y;
+              const float o_hi = hi * cs.x + lo * cs.y;
+              if (is_q) {
+                __nv_bfloat16* qd = a.q_out + (size_t)m * a.q_ld + head * 128;
+                qd[d] = __float2bfloat16_rn(o_lo);
+                qd[d + 64] = __float2bfloat16_rn(o_hi);
+              } else {
+                const int page = a.page_table[pos >> 6];
+                __nv_bfloat16* kd = a.kpool +
+                    ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
+                kd[d] = __float2bfloat16_rn(o_lo);
+                kd[d + 64] = __float2bfloat16_rn(o_hi);
+              }
+            } else {                                       // v: natural order, no rotation
+              const int rel = pr - a.q_rows - a.kv_rows;
+              const int head = rel >> 7, d0 = rel & 127;
               const int page = a.page_table[pos >> 6];
-              __nv_bfloat16* kd = a.kpool +
+              __nv_bfloat16* vd = a.vpool +
                   ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
-              kd[d] = __float2bfloat16_rn(o_lo);
-              kd[d + 64] = __float2bfloat16_rn(o_hi);
-            }
-          } else {                                       // v: natural order, no rotation
-            const int rel = pr - a.q_rows - a.kv_rows;
-            const int head = rel >> 7, d0 = rel & 127;
-            const int page = a.page_table[pos >> 6];
-            __nv_bfloat16* vd = a.vpool +
-                ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
-            vd[d0 + r] = __float2bfloat16_rn(lo);
-            vd[d0 + r + 8] = __float2bfloat16_rn(hi);
-          }
-        }
-      }
-    } else {
-      const int items = TPC * NT * 128;
-      for (int it = tid; it < items; it += kGemmThreads) {
-        const int row = it & 15, tok = (it >> 4) & 7, n = (it >> 7) % NT, tl = (it >> 7) / NT;
-        const int m = n * 8 + tok;
-        const int tl_tile = grp * TPC + tl;
-        if (tl_tile >= a.n_tiles) continue;
-        const int orow = tl_tile * 16 + row;
-        const float v = (m < a.M) ? ksum(tl, n, row, tok) : 0.f;
-        if (EPI == EPI_RESID) {
-          if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] += v;
-        } else if (EPI == EPI_STORE) {
-          if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
-        } else {  // LMHEAD
-          if (m < a.M && a.logits != nullptr && orow < a.n_valid_rows)
-            a.logits[(size_t)m * a.logits_ld + orow] = v;
-          lg[m * (TPC * 16) + tl * 16 + row] = v;
-        }
-      }
-      if (EPI == EPI_LMHEAD) {
-        __syncthreads();
-        if (warp < NT * 8 && warp < a.M) {
-          float bv = -INFINITY;
-          int bi = 0x7fffffff;
-          for (int i = lane; i < TPC * 16; i += 32) {
-            const int orow = grp * TPC * 16 + i;
-            if (orow < a.n_valid_rows) {
-              const float v = lg[warp * (TPC * 16) + i];
-              if (better(v, orow, bv, bi)) { bv = v; bi = orow; }
+              vd[d0 + r] = __float2bfloat16_rn(lo);
+              vd[d0 + r + 8] = __float2bfloat16_rn(hi);
             }
           }
+        }
+      } else {
+        const int items = TPP * NT * 128;
+        for (int itx = etid; itx < items; itx += kEpiThreads) {
+          const int row = itx & 15, tok = (itx >> 4) & 7, n = (itx >> 7) % NT, j = (itx >> 7) / NT;
+          const int m = n * 8 + tok;
+          const int tile = slot * TPP + j;
+          if (tile >= a.n_tiles) continue;
+          const int orow = tile * 16 + row;
+          const float v = (m < a.M) ? ksum(j, n, row, tok) : 0.f;
+          if (EPI == EPI_RESID) {
+            if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] += v;
+          } else if (EPI == EPI_STORE) {
+            if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
+          } else {  // LMHEAD
+            if (m < a.M && a.logits != nullptr && orow < a.n_valid_rows)
+              a.logits[(size_t)m * a.logits_ld + orow] = v;
+            lg[m * (TPP * 16) + j * 16 + row] = v;
+          }
+        }
+        if (EPI == EPI_LMHEAD) {
+          bar_sync(BAR_EPI, kEpiThreads);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+          for (int i = 0; i < kRowsPerEwarp; ++i) {
+            const int m = ewarp + i * kEpiWarps;
+            if (m < NT * 8 && m < a.M) {
+              float bv = -INFINITY;
+              int bi = 0x7fffffff;
+              for (int c = lane; c < TPP * 16; c += 32) {
+                const int orow = slot * TPP * 16 + c;
+                if (orow < a.n_valid_rows && orow < a.n_tiles * 16) {
+                  const float v = lg[m * (TPP * 16) + c];
+                  if (better(v, orow, bv, bi)) { bv = v; bi = orow; }
+                }
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+              }
+              if (better(bv, bi, best_v[i], best_i[i])) { best_v[i] = bv; best_i[i] = bi; }
+            }
           }
-          if (better(bv, bi, best_v, best_i)) { best_v = bv; best_i = bi; }
+          bar_sync(BAR_EPI, kEpiThreads);   // lg is rewritten by the next slot
         }
       }
+      if (slot + 2 * gridDim.x < n_slots) bar_arrive(BAR_EMPTY0 + buf, kWorkThreads);
     }
-    __syncthreads();
-  }
 
-  if (EPI == EPI_LMHEAD) {
-    if (warp < NT * 8 && warp < a.M && lane == 0) {
-      a.part_val[blockIdx.x * kMaxRows + warp] = best_v;
-      a.part_idx[blockIdx.x * kMaxRows + warp] =
-          (best_i == 0x7fffffff) ? 0x7fffffff : best_i + a.vocab_off;
+    if (EPI == EPI_LMHEAD) {
+#pragma unroll
+      for (int i = 0; i < kRowsPerEwarp; ++i) {
+        const int m = ewarp + i * kEpiWarps;
+        if (m < NT * 8 && m < a.M && lane == 0) {
+          a.part_val[blockIdx.x * kMaxRows + m] = best_v[i];
+          a.part_idx[blockIdx.x * kMaxRows + m] =
+              (best_i[i] == 0x7fffffff) ? 0x7fffffff : best_i[i] + a.vocab_off;
+        }
+      }
     }
   }
 }

@@ -142,6 +142,24 @@ class Engine:
             draft=list(out.draft_ids[:out.n_drafted]),
             verified=list(out.verified_ids[:out.n_drafted + 1]), kv_len=out.kv_len)
 
+    KERNEL_CLASSES = ("qkv", "attention", "o_proj", "gate_up", "down", "lm_head", "small", "comm")
+
+    def profile_round(self, d_req: int):
+        """Eager round with per-kernel-class device times (ms) and launch counts."""
+        out = _lib.lsk_round_out()
+        ms = (C.c_float * 8)()
+        cnt = (C.c_int64 * 8)()
+        total = C.c_float()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_profile_round(self._h, d_req, C.byref(out), ms, cnt,
+                                                   C.byref(total)))
+        r = RoundOutput(n_drafted=out.n_drafted, n_matches=out.n_matches,
+                        emitted=list(out.emitted_ids[:out.n_emitted]),
+                        draft=list(out.draft_ids[:out.n_drafted]),
+                        verified=list(out.verified_ids[:out.n_drafted + 1]), kv_len=out.kv_len)
+        return r, dict(zip(self.KERNEL_CLASSES, [float(x) for x in ms])), \
+            dict(zip(self.KERNEL_CLASSES, [int(x) for x in cnt])), float(total.value)
+
     def ar_step(self) -> int:
         tok = C.c_int32()
         with torch.cuda.device(self.device):

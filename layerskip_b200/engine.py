@@ -72,16 +72,12 @@ class Engine:
         if self.tp_size == 1:
             return
         import torch.distributed as dist
+        from .parallel_util import broadcast_bytes
         uid = (C.c_uint8 * 128)()
-        if self.tp_rank == 0:
+        if dist.get_rank(process_group) == 0:
             _lib.check(self._lib.lsk_comm_unique_id(uid))
-        buf = torch.tensor(list(uid), dtype=torch.uint8)
-        backend = dist.get_backend(process_group)
-        if backend == "nccl":
-            buf = buf.to(self.device)
-        dist.broadcast(buf, src=dist.get_global_rank(process_group, 0) if process_group else 0,
-                       group=process_group)
-        arr = (C.c_uint8 * 128)(*buf.cpu().tolist())
+        raw = broadcast_bytes(bytes(uid), 128, src=0, group=process_group, device=self.device)
+        arr = (C.c_uint8 * 128)(*raw)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.lsk_comm_init(self._h, arr))
 

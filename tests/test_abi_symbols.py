@@ -1,0 +1,57 @@
+"""CPU: the shared library loads without a GPU and exports every symbol include/lsk.h declares;
+the ctypes table (layerskip_b200/_lib.py) covers exactly that list."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "lsk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lsk_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_ctypes_table_agree():
+    from layerskip_b200 import _lib
+    assert _header_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_symbol():
+    from layerskip_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    lib = _lib.load()
+    for name in _header_symbols():
+        assert hasattr(lib, name), name
+    assert lib.lsk_abi_version() == 1
+    assert isinstance(lib.lsk_last_error(), bytes)
+
+
+def test_struct_sizes_match_the_header():
+    import ctypes as C
+    from layerskip_b200 import _lib
+    assert C.sizeof(_lib.lsk_config) == 14 * 4
+    assert C.sizeof(_lib.lsk_round_out) == 4 * 4 + 3 * 16 * 4
+    assert C.sizeof(_lib.lsk_weight_desc) == 32
+    assert C.sizeof(_lib.lsk_generation) == 72      # 60 bytes of 32-bit fields, pad to 8, uint64 seed
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from layerskip_b200.engine import Engine
+    from layerskip_b200.weights import ARCHS
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Engine(ARCHS["tiny-mha"])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "layerskip_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn

@@ -1,0 +1,51 @@
+"""CPU, world_size 2, gloo: the N > 1 host plumbing (prompt sharding for replicas, the NCCL
+unique-id broadcast the tensor-parallel engines use, max/sum reductions of bench.py)."""
+import os
+import socket
+
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from layerskip_b200 import parallel_util as pu
+        from layerskip_b200.synthetic import synthetic_prompts
+        prompts = synthetic_prompts(512, 8, 16)
+        mine = pu.shard_prompts(prompts, rank, world)
+        payload = bytes(range(128)) if rank == 0 else b""
+        got = pu.broadcast_bytes(payload, 128, src=0)
+        mx = pu.reduce_scalar(10.0 + rank, "max")
+        sm = pu.reduce_scalar(len(mine), "sum")
+        q.put((rank, [p[0] for p in mine], got == bytes(range(128)), mx, sm))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_plumbing():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from layerskip_b200.synthetic import synthetic_prompts
+    firsts = [p[0] for p in synthetic_prompts(512, 8, 16)]
+    assert res[0][1] == firsts[0::2] and res[1][1] == firsts[1::2]      # disjoint, covering
+    assert all(r[2] for r in res)                                          # same id bytes everywhere
+    assert all(r[3] == 11.0 for r in res) and all(r[4] == 8.0 for r in res)

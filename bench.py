@@ -131,6 +131,61 @@ def measured_peaks():
 # --------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------
+def usable_cpus() -> int:
+    """CPUs this process may really use: affinity mask, capped by the cgroup CPU quota (a box
+    can show 128 cores while the container is throttled to far fewer — running 128 OpenMP
+    threads there is two orders of magnitude slower than running 16)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, quota // period))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+CPU_THREADS = None
+
+
+def cpu_threads() -> int:
+    global CPU_THREADS
+    if CPU_THREADS is None:
+        CPU_THREADS = min(32, usable_cpus())     # batch-1 GEMV is DRAM-bound: 32 threads saturate it
+    return CPU_THREADS
+
+
+class time_limit:
+    """Hard wall-clock bound for the CPU legs (SIGALRM -> TimeoutError between torch ops)."""
+
+    def __init__(self, seconds):
+        self.seconds = int(seconds)
+
+    def __enter__(self):
+        import signal
+
+        def handler(signum, frame):
+            raise TimeoutError(f"CPU leg exceeded {self.seconds} s")
+        self.old = signal.signal(signal.SIGALRM, handler)
+        signal.alarm(self.seconds)
+
+    def __exit__(self, *exc):
+        import signal
+        signal.alarm(0)
+        signal.signal(signal.SIGALRM, self.old)
+        return False
+
+
 def cpu_weights(sd, arch):
     """Oracle weights on the host: fp32 when RAM allows (torch's CPU bf16 matmul is an order of
     magnitude slower than fp32 on these Xeons), else bf16."""
@@ -150,7 +205,7 @@ def cpu_reference_run(args, w, arch, prompts, n_generations, max_steps):
     oracle (CPU restatement of the reference algorithm).  Returns (tokens, seconds, acc)."""
     import torch
     from oracle import llama_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     tokens, seconds, rates = 0, 0.0, []
     with torch.inference_mode():
         for i in range(n_generations):
@@ -199,15 +254,20 @@ def run_reference_arm(args):
     model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=args.exit_layer, device=dev)
     sd = model.state_dict(dtype=torch.bfloat16, device="cpu")
     prompts = synthetic_prompts(arch.vocab, 8, args.prompt_len)
-    cores = os.cpu_count() or 1
     # bounded sample: same prompt length, a short continuation (CPU runs ~0.1-0.6 s per round)
+    cores = cpu_threads()
     w, w_dtype = cpu_weights(sd, arch)
     del sd
-    budget = 120.0 / max(1, args.steps)           # whole arm: about two minutes of CPU time
-    cpu_steps, _probe = cpu_sized_sample(args, w, arch, prompts, budget)   # doubles as warm-up
-    if args.cpu_max_steps:
-        cpu_steps = args.cpu_max_steps
-    tokens, seconds, acc = cpu_reference_run(args, w, arch, prompts, max(1, args.steps), cpu_steps)
+    budget = 100.0 / max(1, args.steps)           # whole arm: under two minutes of CPU time
+    try:
+        with time_limit(170):
+            cpu_steps, _probe = cpu_sized_sample(args, w, arch, prompts, budget)   # doubles as warm-up
+            if args.cpu_max_steps:
+                cpu_steps = args.cpu_max_steps
+            tokens, seconds, acc = cpu_reference_run(args, w, arch, prompts, max(1, args.steps), cpu_steps)
+    except TimeoutError as exc:
+        print(json.dumps({"impl": "reference", "unavailable": f"CPU run did not finish: {exc}"}), flush=True)
+        return
     value = tokens / seconds
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -395,10 +455,11 @@ def run_b200_arm(args):
             sd = model.state_dict(dtype=torch.bfloat16, device="cpu")
             w, w_dtype = cpu_weights(sd, arch)
             del sd
-            cores = os.cpu_count() or 1
+            cores = cpu_threads()
             t0 = time.perf_counter()
-            n_cpu, _probe = cpu_sized_sample(args, w, arch, prompts, 20.0)
-            toks, secs, _acc = cpu_reference_run(args, w, arch, prompts, 1, n_cpu)
+            with time_limit(100):
+                n_cpu, _probe = cpu_sized_sample(args, w, arch, prompts, 20.0)
+                toks, secs, _acc = cpu_reference_run(args, w, arch, prompts, 1, n_cpu)
             cpu_baseline = {"value": toks / secs, "unit": UNIT, "cores": cores, "kind": "port",
                             "cpu": cpu_model_name(),
                             "sample": f"1 generation x {n_cpu} tokens, prompt {args.prompt_len} ids "
@@ -406,7 +467,7 @@ def run_b200_arm(args):
                                       f"{time.perf_counter() - t0:.1f} s of CPU work incl. sizing probe"}
             del w
         except Exception as exc:  # pragma: no cover
-            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                             "sample": f"failed: {exc!r}"}
 
     if rank == 0 and not args.no_extra and world == 1:

@@ -145,7 +145,9 @@ typedef enum {
   LSK_DBG_HIDDEN = 0,        /* fp32 [16, hidden] residual-stream rows of the last launch     */
   LSK_DBG_LOGITS = 1,        /* fp32 [16, vocab_local] (needs LSK_FLAG_KEEP_LOGITS)           */
   LSK_DBG_KROW = 2,          /* bf16->fp32 K cache row: layer, index = kv_head*max_ctx + pos  */
-  LSK_DBG_VROW = 3
+  LSK_DBG_VROW = 3,
+  LSK_DBG_PROBS_DRAFT = 4,   /* fp32 [16, vocab] warped (T, top-k, top-p) draft distributions     */
+  LSK_DBG_PROBS_VERIFY = 5   /* fp32 [16, vocab] warped verifier distributions of the last round */
 } lsk_debug_what;
 int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index,
                    float* dst_host, int64_t n_floats);

@@ -20,7 +20,8 @@ LSK_FLAG_NO_GRAPH = 4
 (LSK_W_EMBED, LSK_W_FINAL_NORM, LSK_W_LM_HEAD, LSK_W_LN1, LSK_W_Q, LSK_W_K, LSK_W_V, LSK_W_O,
  LSK_W_LN2, LSK_W_GATE, LSK_W_UP, LSK_W_DOWN) = range(12)
 
-LSK_DBG_HIDDEN, LSK_DBG_LOGITS, LSK_DBG_KROW, LSK_DBG_VROW = range(4)
+LSK_DBG_HIDDEN, LSK_DBG_LOGITS, LSK_DBG_KROW, LSK_DBG_VROW, LSK_DBG_PROBS_DRAFT, \
+    LSK_DBG_PROBS_VERIFY = range(6)
 
 
 class LskLibraryError(RuntimeError):

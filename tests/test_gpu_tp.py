@@ -1,0 +1,79 @@
+"""GPU (needs >= 2 devices): tensor-parallel engine, one process per GPU, NCCL all-reduce after
+O-proj / down-proj only.  Checked against the golden reference traces (margin
+gate) and for exact speculative == autoregressive on the sharded engine."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, case_names, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from layerskip_b200 import GenerationConfig
+        from layerskip_b200.strategy import (B200AutoRegressiveGenerationStrategy,
+                                             B200SelfSpeculativeGenerationStrategy)
+        from oracle import llama_oracle as orc
+        from tests import golden_util as gu
+        from tests import parity_util as pu
+        from tests.test_gpu_engine import _Model
+        spec = B200SelfSpeculativeGenerationStrategy(max_ctx=512, tp_rank=rank, tp_size=world)
+        ar = B200AutoRegressiveGenerationStrategy(engine_cache=spec.engines)
+        out = {}
+        for name in case_names:
+            case = next(c for c in gu.spec_cases() if c["name"] == name)
+            dims, sd = gu.state_dict_for(case)
+            model = _Model(dims, sd)
+            w = orc.weights_from_state_dict(dims, sd)
+
+            def generate(prompt, n):
+                cfg = GenerationConfig(**{**case["cfg"], "max_steps": n})
+                return spec.generate_token_ids(model, prompt, case["eos"], cfg).predicted_tokens
+
+            flips, gaps = pu.check_stream(w, case["prompt"], case["reference"]["spec_tokens"], generate)
+            s = spec.generate_token_ids(model, case["prompt"], case["eos"], GenerationConfig(**case["cfg"]))
+            a = ar.generate_token_ids(model, case["prompt"], case["eos"],
+                                      GenerationConfig(**{**case["cfg"], "exit_layer": -1,
+                                                          "num_speculations": -1}))
+            out[name] = dict(flips=flips, gaps=gaps, spec=s.predicted_tokens, ar=a.predicted_tokens,
+                             acc=s.acceptance_rate)
+        q.put((rank, out))
+        spec.engines.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tensor_parallel_2gpu_matches_reference_and_is_self_consistent():
+    import torch.multiprocessing as mp
+    names = ["gqa128_a0.1", "mha128_a0.1", "gqa128_a0.05_long"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, names, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for name in names:
+        r0, r1 = res[0][name], res[1][name]
+        assert r0["spec"] == r1["spec"] and r0["ar"] == r1["ar"]        # ranks agree
+        assert r0["spec"] == r0["ar"]                                   # exact on the sharded engine
+        assert r0["flips"] <= 4, r0["gaps"]

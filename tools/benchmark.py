@@ -1,0 +1,10 @@
+#!/usr/bin/env python
+"""Same flags as the reference's benchmark.py (see layerskip_b200/cli.py)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from layerskip_b200.cli import main_benchmark
+
+if __name__ == "__main__":
+    main_benchmark()

@@ -36,6 +36,7 @@ typedef enum {
 #define LSK_FLAG_KEEP_LOGITS 1u  /* also store fp32 logits (needed for sampling / debug reads) */
 #define LSK_FLAG_NO_PDL 2u       /* disable programmatic dependent launch                    */
 #define LSK_FLAG_NO_GRAPH 4u     /* launch kernels eagerly instead of replaying CUDA graphs  */
+#define LSK_FLAG_MEGAKERNEL 8u   /* opt in: ONE persistent cooperative kernel per round / AR step     */
 
 /* Llama architecture + engine sizing.  Replaces what the reference reads off the HF model
  * object (`model.config`, generate.py:54-67). */

@@ -11,9 +11,12 @@
 // Partials (m, l, O) are merged in fixed order: 4 warps inside the CTA, then the splits by the
 // last CTA to finish for that kv head (atomic ticket).  Deterministic.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lsk {
+namespace cg = cooperative_groups;
 
 constexpr int kAttnThreads = 128;
 constexpr int kKeyGroup = 64;                 // keys per CTA iteration (one KV page)
@@ -40,19 +43,26 @@ struct AttnArgs {
   int* tickets;                // [kv]
 };
 
-__global__ void __launch_bounds__(kAttnThreads)
-attn_splitkv_kernel(const AttnArgs a) {
-  __shared__ __align__(128) unsigned char sm_raw[2 * kKeyGroup * kKvRowBytes];
-  __shared__ int s_last;
+constexpr int kAttnTeamSmem = 2 * kKeyGroup * kKvRowBytes + 128;   // K/V staging + flag
+constexpr int BAR_TEAM0 = 8;                                       // named barriers 8..10
+
+__device__ __forceinline__ void team_sync(int bar_id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kAttnThreads) : "memory");
+}
+
+// One (kv head, split) work item, executed by a TEAM of 4 warps (`tid` in 0..127) that owns
+// `sm_raw` (kAttnTeamSmem bytes) and named barrier `bar_id`.  Used by the stand-alone kernel
+// (one team per CTA) and by the step megakernel (three teams per CTA).
+// Phase 1 of a (kv head, split) work item: online-softmax partial (m, l, O) of this split's key
+// groups for every query row, 4 warps merged in fixed order, written to po[row][128] /
+// pml[row][2] (global scratch OR shared memory — the cluster kernel keeps it on chip).
+__device__ __forceinline__ void attn_partial(const AttnArgs& a, int kvh, int split,
+                                             unsigned char* sm_raw, int tid, int bar_id,
+                                             float* __restrict__ po_base, float* __restrict__ pml_base) {
   unsigned char* ks = sm_raw;
   unsigned char* vs = sm_raw + kKeyGroup * kKvRowBytes;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int kvh = blockIdx.x, split = blockIdx.y;
-
-  pdl_launch_dependents();
-  pdl_wait();
 
   const int base = *a.base_len + a.pos_off;          // position of token row 0
   const int n_keys = base + a.M;                      // keys visible to the last row
@@ -87,7 +97,7 @@ attn_splitkv_kernel(const AttnArgs a) {
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
     for (int kg = split; kg < n_kgroups; kg += a.n_splits) {
-      __syncthreads();   // previous iteration's readers are done with ks / vs
+      team_sync(bar_id);   // previous iteration's readers are done with ks / vs
       {
         const int page = a.page_table[kg];   // kKeyGroup == kPageTokens
         const __nv_bfloat16* kp = a.kpool + (size_t)(page * a.n_kv_heads + kvh) * kPageTokens * kHeadDim;
@@ -103,7 +113,7 @@ attn_splitkv_kernel(const AttnArgs a) {
           *reinterpret_cast<uint4*>(vs + key * kKvRowBytes + ch * 16) = vv4;
         }
       }
-      __syncthreads();
+      team_sync(bar_id);
 
       // ---- S = Q K^T for this warp's 16 keys (two n8 tiles)
       float s[2][4];
@@ -181,7 +191,7 @@ attn_splitkv_kernel(const AttnArgs a) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    __syncthreads();   // everyone is done with ks / vs: reuse as merge buffer
+    team_sync(bar_id);   // everyone is done with ks / vs: reuse as merge buffer
     float* mo = reinterpret_cast<float*>(sm_raw);            // [4 warps][16 rows][128]
     float* mml = mo + 4 * 16 * kHeadDim;                      // [4][16][2]
 #pragma unroll
@@ -197,7 +207,7 @@ attn_splitkv_kernel(const AttnArgs a) {
       mml[(warp * 16 + g + 8) * 2] = m1;
       mml[(warp * 16 + g + 8) * 2 + 1] = l1;
     }
-    __syncthreads();
+    team_sync(bar_id);
     {
       // thread -> (row = tid / 8, 16 dims = (tid % 8) * 16 ..)
       const int row = tid >> 3, dseg = (tid & 7) * 16;
@@ -214,28 +224,39 @@ attn_splitkv_kernel(const AttnArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] += mo[(w * 16 + row) * kHeadDim + dseg + i] * f;
       }
-      const size_t prow = ((size_t)(kvh * a.n_splits + split) * a.rows_pad + rb * 16 + row);
-      float* po = a.part_o + prow * kHeadDim + dseg;
+      const size_t prow = (size_t)(rb * 16 + row);
+      float* po = po_base + prow * kHeadDim + dseg;
 #pragma unroll
       for (int i = 0; i < 16; i += 4)
         *reinterpret_cast<float4*>(po + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
       if ((tid & 7) == 0) {
-        a.part_ml[prow * 2] = mm;
-        a.part_ml[prow * 2 + 1] = ll;
+        pml_base[prow * 2] = mm;
+        pml_base[prow * 2 + 1] = ll;
       }
     }
-    __syncthreads();   // merge buffer free before the next row block refills ks / vs
+    team_sync(bar_id);   // merge buffer free before the next row block refills ks / vs
   }
 
+}
+
+// One (kv head, split) work item with the GLOBAL-scratch merge: partial -> global, then the last
+// team to finish for this kv head (atomic ticket) merges the splits in fixed order.  Used by the
+// step megakernel (three teams per CTA) and as the non-cluster fallback kernel.
+__device__ __forceinline__ void attn_team(const AttnArgs& a, int kvh, int split,
+                                          unsigned char* sm_raw, int tid, int bar_id) {
+  volatile int* s_last = reinterpret_cast<volatile int*>(sm_raw + 2 * kKeyGroup * kKvRowBytes);
+  const size_t blk = (size_t)(kvh * a.n_splits + split) * a.rows_pad;
+  attn_partial(a, kvh, split, sm_raw, tid, bar_id, a.part_o + blk * kHeadDim, a.part_ml + blk * 2);
+  const int R = a.group * a.M;
   // ---- cross-split merge by the last CTA of this kv head
   __threadfence();
-  __syncthreads();
+  team_sync(bar_id);
   if (tid == 0) {
     const int tk = atomicAdd(&a.tickets[kvh], 1);
-    s_last = (tk == a.n_splits - 1);
+    *s_last = (tk == a.n_splits - 1);
   }
-  __syncthreads();
-  if (!s_last) return;
+  team_sync(bar_id);
+  if (!*s_last) return;
   __threadfence();
   for (int item = tid; item < R * 8; item += kAttnThreads) {
     const int row = item >> 3, dseg = (item & 7) * 16;
@@ -267,6 +288,73 @@ attn_splitkv_kernel(const AttnArgs a) {
       *reinterpret_cast<uint32_t*>(op + i) = pack_bf16x2(acc[i] * inv, acc[i + 1] * inv);
   }
   if (tid == 0) a.tickets[kvh] = 0;
+}
+
+// Fixed-order merge of the splits' partials for one (row, 16-dim segment); `ml(s)` / `o(s)` return
+// split s's (m, l) pair and O segment — from global scratch or from a peer CTA's shared memory.
+template <typename FML, typename FO>
+__device__ __forceinline__ void merge_splits_write(const AttnArgs& a, int kvh, int row, int dseg,
+                                                   FML ml, FO o) {
+  float mm = -INFINITY;
+  for (int s = 0; s < a.n_splits; ++s) mm = fmaxf(mm, ml(s)[0]);
+  float ll = 0.f;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int s = 0; s < a.n_splits; ++s) {
+    const float* mls = ml(s);
+    const float ms = mls[0];
+    const float f = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+    ll += mls[1] * f;
+    const float4* po = reinterpret_cast<const float4*>(o(s));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = po[i];
+      acc[4 * i] += v.x * f; acc[4 * i + 1] += v.y * f;
+      acc[4 * i + 2] += v.z * f; acc[4 * i + 3] += v.w * f;
+    }
+  }
+  const float inv = 1.f / ll;
+  const int tok = row / a.group, hq = kvh * a.group + row % a.group;
+  __nv_bfloat16* op = a.out + (size_t)tok * a.out_ld + hq * kHeadDim + dseg;
+#pragma unroll
+  for (int i = 0; i < 16; i += 2)
+    *reinterpret_cast<uint32_t*>(op + i) = pack_bf16x2(acc[i] * inv, acc[i + 1] * inv);
+}
+
+// Cluster kernel: the n_splits CTAs of one kv head form a thread-block cluster; partials stay in
+// shared memory and are merged through DISTRIBUTED shared memory after one cluster barrier —
+// no global scratch, no __threadfence, no atomic ticket, no re-read (the global-merge chain cost
+// 3-4 dependent memory round trips of the ~7 on this kernel's critical path).
+__global__ void __launch_bounds__(kAttnThreads)
+attn_cluster_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  float* po = reinterpret_cast<float*>(dsm + kAttnTeamSmem);
+  float* pml = po + (size_t)a.rows_pad * kHeadDim;
+  const int kvh = blockIdx.x, split = blockIdx.y;          // cluster = all splits of one kv head
+  const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  attn_partial(a, kvh, split, dsm, tid, BAR_TEAM0, po, pml);
+  cluster.sync();
+  const int R = a.group * a.M;
+  for (int item = split * kAttnThreads + tid; item < R * 8; item += a.n_splits * kAttnThreads) {
+    const int row = item >> 3, dseg = (item & 7) * 16;
+    merge_splits_write(
+        a, kvh, row, dseg,
+        [&](int s) { return (const float*)cluster.map_shared_rank(pml, s) + row * 2; },
+        [&](int s) { return (const float*)cluster.map_shared_rank(po, s) + (size_t)row * kHeadDim + dseg; });
+  }
+  cluster.sync();      // nobody leaves while a peer may still read its partials
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+attn_splitkv_kernel(const AttnArgs a) {
+  __shared__ __align__(128) unsigned char sm_raw[kAttnTeamSmem];
+  pdl_launch_dependents();
+  pdl_wait();
+  attn_team(a, blockIdx.x, blockIdx.y, sm_raw, threadIdx.x, BAR_TEAM0);
 }
 
 }  // namespace lsk

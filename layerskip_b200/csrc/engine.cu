@@ -19,6 +19,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm_skinny.cuh"
+#include "megakernel.cuh"
 #include "misc_kernels.cuh"
 #include "sampling.cuh"
 
@@ -142,6 +143,20 @@ struct lsk_engine {
   int64_t capture_launches = 0;        // launches recorded while capturing the current graph
   std::map<long long, int64_t> graph_launches;
   float last_ms = 0.f;
+  // step megakernel: when `recording` is set the enqueue_* helpers append stage descriptors
+  // instead of launching kernels; programs live in device memory, one per graph key
+  bool use_mega = false;               // opt-in (LSK_FLAG_MEGAKERNEL / LSK_MEGA=1): measured slower, see DESIGN.md
+  bool attn_cluster = true;            // attention: cluster launch + DSMEM merge of the splits
+  int mega_ring = 6;                   // ring stages of the megakernel (96 KiB)
+  std::vector<StageDesc>* recording = nullptr;
+  bool record_failed = false;
+  std::map<long long, StageDesc*> programs;
+  std::map<long long, int> program_len;
+  unsigned int* grid_counter = nullptr;
+  unsigned long long* timeline = nullptr;   // LSK_MEGA_TIMELINE=1: per-stage start times (CTA 0)
+  std::map<long long, std::vector<int>> program_kinds;
+  double tl_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long tl_rounds = 0;
   // per-kernel-class timing (lsk_profile_round): events around every launch, eager mode
   bool profiling = false;
   int cur_class = 0;
@@ -200,7 +215,9 @@ struct GemmSched {
   size_t smem = 0;
   bool ok = false;
 };
-static GemmSched plan_sched(int NT, int pro, int epi, const GemmPlan& p, int sm_count) {
+// fixed_ring == 0: stand-alone kernel, ring as deep as shared memory allows.
+// fixed_ring  > 0: megakernel stage, the scratch layout must fit behind a ring of that depth.
+static GemmSched plan_sched(int NT, int pro, int epi, const GemmPlan& p, int sm_count, int fixed_ring = 0) {
   GemmSched best;
   for (int want = 1; want <= 16; ++want) {
     if (pro == PRO_RMS && want > 1) break;          // RMSNorm needs the whole row resident
@@ -208,21 +225,35 @@ static GemmSched plan_sched(int NT, int pro, int epi, const GemmPlan& p, int sm_
     if (want > 1) kc = (kc + kStageSbs - 1) / kStageSbs * kStageSbs;
     const int n_chunks = (p.nsb + kc - 1) / kc;
     const int tpp = n_chunks > 1 ? kMaxTilesPerPass : 1;
-    for (int st = kMaxStages; st >= 2; --st) {
-      const GemmSmem L = gemm_smem_layout(NT, kc * 32, tpp, st, epi);
-      if (L.total <= (size_t)kSmemMax) {
+    const GemmScratch L = gemm_scratch_layout(NT, kc * 32, tpp, epi);
+    const int st_hi = fixed_ring > 0 ? fixed_ring : kMaxStages;
+    const int st_lo = fixed_ring > 0 ? fixed_ring : 2;
+    for (int st = st_hi; st >= st_lo; --st) {
+      if (gemm_smem_total(st, L.total) <= (size_t)kSmemMax) {
         if (!best.ok || st > best.n_stages) {
           best.ok = true; best.tpp = tpp; best.n_chunks = n_chunks; best.kc_sbs = kc;
-          best.n_stages = st; best.smem = L.total;
+          best.n_stages = st; best.smem = gemm_smem_total(st, L.total);
         }
         break;
       }
     }
-    if (best.ok && best.n_stages >= 5) break;       // >= 80 KiB in flight per SM: enough
+    if (best.ok && (fixed_ring > 0 || best.n_stages >= 5)) break;   // >= 80 KiB in flight per SM
   }
   if (best.ok) {
     const int n_slots = (p.n_tiles + best.tpp - 1) / best.tpp;
     best.grid = n_slots < sm_count ? n_slots : sm_count;
+    // Tile quantisation: with g CTAs the kernel lasts ceil(n_slots / g) slot-times.  Among the
+    // CTA counts that reach the minimum number of waves, take the SMALLEST one that wastes the
+    // fewest slots (e.g. 768 tiles: 128 CTAs x 6 instead of 148 CTAs of which 28 run a 6th tile
+    // alone) — the TMA ring lets ~85 % of the SMs saturate HBM (LSK_GRID_EVEN=0 disables).
+    static const bool even = !(getenv("LSK_GRID_EVEN") && atoi(getenv("LSK_GRID_EVEN")) == 0);
+    if (even && fixed_ring == 0 && n_slots > sm_count) {
+      const int waves = (n_slots + sm_count - 1) / sm_count;
+      int g = (n_slots + waves - 1) / waves;          // smallest CTA count with that many waves
+      const int lo = sm_count * 4 / 5;
+      if (g < lo) g = lo;
+      best.grid = g;
+    }
   }
   return best;
 }
@@ -251,7 +282,20 @@ static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
 
 template <int PRO, int EPI>
 static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
-  if (a.M <= 8) return launch_gemm_t<1, PRO, EPI>(e, p, a);
+  const int NT = a.M <= 8 ? 1 : 2;
+  if (e->recording) {               // megakernel program: describe the stage instead of launching
+    const GemmSched sc = plan_sched(NT, PRO, EPI, p, e->sm_count, e->mega_ring);
+    if (!sc.ok) { e->record_failed = true; return LSK_OK; }
+    StageDesc d{};
+    d.kind = ST_GEMM; d.nt = NT; d.pro = PRO; d.epi = EPI; d.barrier_before = 1;
+    a.n_tiles = p.n_tiles; a.nsb = p.nsb; a.K = p.K;
+    a.tiles_per_pass = sc.tpp; a.n_chunks = sc.n_chunks; a.kc_sbs = sc.kc_sbs; a.n_stages = e->mega_ring;
+    a.next_W = nullptr; a.next_bytes = 0;
+    d.g = a;
+    e->recording->push_back(d);
+    return LSK_OK;
+  }
+  if (NT == 1) return launch_gemm_t<1, PRO, EPI>(e, p, a);
   if (plan_sched(2, PRO, EPI, p, e->sm_count).ok) return launch_gemm_t<2, PRO, EPI>(e, p, a);
   return fail(LSK_ERR_INVALID, "%d token rows need the 16-row kernel, which does not fit next to K=%d "
               "(hidden sizes > 4096 support at most 8 rows, i.e. num_speculations <= 7)", a.M, p.K);
@@ -295,7 +339,40 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.scale = 1.0f / sqrtf((float)c.head_dim);
     a.part_o = e->part_o; a.part_ml = e->part_ml; a.rows_pad = e->group * 16;
     a.tickets = e->tickets;
-    CU(launch(e, attn_splitkv_kernel, dim3(e->kv_heads_l, e->n_splits), dim3(kAttnThreads), 0, a));
+    if (e->recording) {
+      StageDesc d{};
+      d.kind = ST_ATTN; d.barrier_before = 1; d.a = a;
+      e->recording->push_back(d);
+    } else if (e->attn_cluster) {
+      // the splits of one kv head = one thread-block cluster (DSMEM merge)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(e->kv_heads_l, e->n_splits);
+      cfg.blockDim = dim3(kAttnThreads);
+      cfg.dynamicSmemBytes = kAttnTeamSmem + (size_t)a.rows_pad * (kHeadDim + 2) * 4;
+      cfg.stream = e->stream;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = e->n_splits; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = e->use_pdl ? 2 : 1;
+      e->launches += 1;
+      e->capture_launches += 1;
+      if (!e->profiling) {
+        CU(cudaLaunchKernelEx(&cfg, attn_cluster_kernel, a));
+      } else {
+        cudaEvent_t ea, eb;
+        cudaEventCreate(&ea); cudaEventCreate(&eb);
+        cudaEventRecord(ea, e->stream);
+        cudaError_t err = cudaLaunchKernelEx(&cfg, attn_cluster_kernel, a);
+        cudaEventRecord(eb, e->stream);
+        e->prof_events.push_back({e->cur_class, {ea, eb}});
+        CU(err);
+      }
+    } else {
+      CU(launch(e, attn_splitkv_kernel, dim3(e->kv_heads_l, e->n_splits), dim3(kAttnThreads), 0, a));
+    }
   }
   {  // O projection (+ residual, or all-reduce then residual under TP)
     e->cur_class = CLS_O;
@@ -346,6 +423,71 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
   return LSK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// small stages: launched as kernels, or recorded into a megakernel program
+// ---------------------------------------------------------------------------------------------
+static int emit_embed(lsk_engine* e, const int* ids, float* rows, int n_rows) {
+  const lsk_config& c = e->cfg;
+  e->cur_class = CLS_MISC;
+  if (e->recording) {
+    StageDesc d{};
+    d.kind = ST_EMBED; d.barrier_before = 1;
+    d.m.embed = e->embed; d.m.hidden = c.hidden; d.m.ids = ids; d.m.rows = rows; d.m.row_ld = c.hidden;
+    d.m.n_rows = n_rows;
+    e->recording->push_back(d);
+    return LSK_OK;
+  }
+  CU(launch(e, embed_tokens_kernel, dim3(n_rows), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+            ids, rows, c.hidden));
+  return LSK_OK;
+}
+static const float* cand_val_ptr(lsk_engine* e);
+static const int* cand_idx_ptr(lsk_engine* e);
+static int n_cand(lsk_engine* e);
+static int emit_finalize(lsk_engine* e, int slot, float* dst_row) {
+  const lsk_config& c = e->cfg;
+  e->cur_class = CLS_MISC;
+  if (e->recording) {
+    StageDesc d{};
+    d.kind = ST_FINALIZE; d.barrier_before = 1;
+    d.m.cand_val = e->cand_val; d.m.cand_idx = e->cand_idx; d.m.n_cand = e->sm_count;
+    d.m.st = e->state; d.m.slot = slot; d.m.embed = e->embed; d.m.hidden = c.hidden; d.m.dst_row = dst_row;
+    e->recording->push_back(d);
+    return LSK_OK;
+  }
+  CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
+            e->state, slot, (const __nv_bfloat16*)e->embed, c.hidden, dst_row));
+  return LSK_OK;
+}
+static int emit_accept(lsk_engine* e, int d_spec, int seq) {
+  e->cur_class = CLS_MISC;
+  if (e->recording) {
+    StageDesc d{};
+    d.kind = ST_ACCEPT; d.barrier_before = 1;
+    d.m.cand_val = e->cand_val; d.m.cand_idx = e->cand_idx; d.m.n_cand = e->sm_count;
+    d.m.st = e->state; d.m.d = d_spec; d.m.gp = e->gen_dev; d.m.res = e->res_dev;
+    e->recording->push_back(d);
+    return LSK_OK;
+  }
+  CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d_spec,
+            e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
+  return LSK_OK;
+}
+static int emit_ar_commit(lsk_engine* e, int seq) {
+  e->cur_class = CLS_MISC;
+  if (e->recording) {
+    StageDesc d{};
+    d.kind = ST_AR_COMMIT; d.barrier_before = 1;
+    d.m.cand_val = e->cand_val; d.m.cand_idx = e->cand_idx; d.m.n_cand = e->sm_count;
+    d.m.st = e->state; d.m.res = e->res_dev;
+    e->recording->push_back(d);
+    return LSK_OK;
+  }
+  CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
+            e->res_dev, seq));
+  return LSK_OK;
+}
+
 // final RMSNorm + LM head on rows [row0, row0+M): arg-max candidates (and optional logits).
 // (llama_model_utils.py:204-205, 271-273, 386-387).  Afterwards e->cand_* / n_cand() hold one
 // (value, index) per candidate per row.
@@ -383,9 +525,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   const lsk_config& c = e->cfg;
   const int* len = &e->state->len;
   // row 0 <- embedding of the pending token (self_speculation_generator.py:122, input_ids)
-  e->cur_class = CLS_MISC;
-  CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
-            (const int*)&e->state->tok[0], e->hidden, c.hidden));
+  TRY(emit_embed(e, &e->state->tok[0], e->hidden, 1));
   // draft loop (:127-148): step i runs layers [0,E) on row i at position len+i, then the shared
   // head; its arg-max becomes tok[i+1] and is embedded into row i+1.
   const size_t qkv_bytes = (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2;
@@ -401,9 +541,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
     TRY(enqueue_lm_head(e, i, 1, e->layers[0].wqkv, qkv_bytes));
     e->cur_class = CLS_MISC;
     if (!e->gen.sample) {
-      CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
-                e->state, 1 + i, (const __nv_bfloat16*)e->embed, c.hidden,
-                e->hidden + (size_t)(i + 1) * c.hidden));
+      TRY(emit_finalize(e, 1 + i, e->hidden + (size_t)(i + 1) * c.hidden));
     } else {
       // decode_next_token sampling branch (llama_model_utils.py:123-131): keep the warped
       // distribution of draft i (needed by the rejection test), draw tok[i+1], embed it.
@@ -425,8 +563,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   TRY(enqueue_lm_head(e, 0, d + 1, e->layers[0].wqkv, qkv_bytes));
   e->cur_class = CLS_MISC;
   if (!e->gen.sample) {
-    CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d,
-              e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
+    TRY(emit_accept(e, d, seq));
   } else {
     CU(launch(e, warp_and_sample_kernel, dim3(d + 1), dim3(kSampleThreads), 0, (const float*)e->logits,
               e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
@@ -441,8 +578,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
 static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
   const lsk_config& c = e->cfg;
   const int* len = &e->state->len;
-  CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
-            (const int*)&e->state->tok[0], e->hidden, c.hidden));
+  TRY(emit_embed(e, &e->state->tok[0], e->hidden, 1));
   const size_t qkv_bytes = (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2;
   const size_t lm_bytes = (size_t)e->vocab_l_pad * c.hidden * 2;
   for (int l = 0; l < n_layers_run; ++l) {
@@ -452,8 +588,7 @@ static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
   TRY(enqueue_lm_head(e, 0, 1, e->layers[0].wqkv, qkv_bytes));
   e->cur_class = CLS_MISC;
   if (!e->gen.sample) {
-    CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
-              e->res_dev, seq));
+    TRY(emit_ar_commit(e, seq));
   } else {
     CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->logits,
               e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
@@ -497,6 +632,92 @@ static int run_cached(lsk_engine* e, long long key, F enqueue) {
   return LSK_OK;
 }
 
+// Megakernel path: record the stage program once per key, then replay
+//   memset(grid barrier counter) -> ONE cooperative launch of step_megakernel.
+// Returns 1 when the shape cannot be served by the megakernel (caller falls back).
+template <typename F>
+static int run_mega(lsk_engine* e, long long key, F enqueue) {
+  auto pit = e->programs.find(key);
+  if (pit == e->programs.end()) {
+    std::vector<StageDesc> prog;
+    e->recording = &prog;
+    e->record_failed = false;
+    int st = enqueue();
+    e->recording = nullptr;
+    if (st != LSK_OK) return st;
+    if (e->record_failed || prog.empty()) {
+      e->programs[key] = nullptr;
+      e->program_len[key] = 0;
+      return 1;
+    }
+    prog[0].barrier_before = 0;
+    StageDesc* dev = nullptr;
+    CU(cudaMalloc((void**)&dev, prog.size() * sizeof(StageDesc)));
+    CU(cudaMemcpy(dev, prog.data(), prog.size() * sizeof(StageDesc), cudaMemcpyHostToDevice));
+    e->programs[key] = dev;
+    e->program_len[key] = (int)prog.size();
+    {
+      std::vector<int> kinds;
+      for (auto& d : prog) kinds.push_back(d.kind == ST_GEMM ? 10 + d.epi : d.kind);
+      e->program_kinds[key] = kinds;
+    }
+    pit = e->programs.find(key);
+  }
+  if (pit->second == nullptr) return 1;
+  StageDesc* dev = pit->second;
+  const int n = e->program_len[key];
+  const int rc = run_cached(e, key | (1LL << 40), [&]() -> int {
+    CU(cudaMemsetAsync(e->grid_counter, 0, sizeof(unsigned int), e->stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(e->sm_count);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kSmemMax;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = getenv("LSK_MEGA_NO_COOP") ? 0 : 1;
+    e->launches += 1;
+    e->capture_launches += 1;
+    CU(cudaLaunchKernelEx(&cfg, step_megakernel, (const StageDesc*)dev, n, e->grid_counter, e->mega_ring,
+                          e->timeline));
+    return LSK_OK;
+  });
+  if (rc == LSK_OK && e->timeline && n < 4096) {
+    std::vector<unsigned long long> t(n + 1);
+    CU(cudaMemcpy(t.data(), e->timeline, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    const std::vector<int>& kinds = e->program_kinds[key];
+    for (int i = 0; i < n; ++i) {
+      const int k = kinds[i];
+      const int slot = k >= 10 ? (k - 10 + 3) : (k == ST_ATTN ? 1 : 2);   // 1 attn, 2 small, 3.. gemm by epilogue
+      e->tl_ns[slot & 7] += (double)(t[i + 1] - t[i]);
+    }
+    e->tl_rounds += 1;
+    if (getenv("LSK_MEGA_PHASES") && e->tl_rounds == 8) {   // one detailed dump (SM-clock cycles)
+      std::vector<unsigned long long> ph((size_t)4 * 4096 * 4);
+      CU(cudaMemcpy(ph.data(), e->timeline + 4097, ph.size() * 8, cudaMemcpyDeviceToHost));
+      const int ctas[4] = {0, 27, 100, e->sm_count - 1};
+      fprintf(stderr, "[lsk phases] stage kind | per CTA: prologue, consume, cta-done wait, barrier wait (cycles)\n");
+      for (int i = 0; i < n && i < 48; ++i) {
+        fprintf(stderr, "  s%02d k%02d |", i, kinds[i]);
+        for (int cs = 0; cs < 4; ++cs) {
+          const unsigned long long* a = &ph[((size_t)cs * 4096 + i) * 4];
+          const unsigned long long* nx = &ph[((size_t)cs * 4096 + i + 1) * 4];
+          if (kinds[i] >= 10)
+            fprintf(stderr, " c%03d: %6lld %6lld %6lld %6lld |", ctas[cs], (long long)(a[1] - a[0]),
+                    (long long)(a[2] - a[1]), (long long)(a[3] - a[2]), (long long)(nx[0] - a[3]));
+          else
+            fprintf(stderr, " c%03d: %6s %6lld %6s %6lld |", ctas[cs], "-", (long long)(a[3] - a[0]), "-",
+                    (long long)(nx[0] - a[3]));
+        }
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  return rc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -525,6 +746,9 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   e->use_pdl = !(c.flags & LSK_FLAG_NO_PDL);
   e->use_graph = !(c.flags & LSK_FLAG_NO_GRAPH);
   e->keep_logits = (c.flags & LSK_FLAG_KEEP_LOGITS) != 0;
+  e->use_mega = ((c.flags & LSK_FLAG_MEGAKERNEL) || getenv("LSK_MEGA")) && !getenv("LSK_NO_MEGA");
+  e->attn_cluster = !getenv("LSK_NO_ATTN_CLUSTER");
+  if (const char* env = getenv("LSK_MEGA_RING")) { int v = atoi(env); if (v >= 3 && v <= kMaxStages) e->mega_ring = v; }
   e->heads_l = c.n_heads / c.tp_size;
   e->kv_heads_l = c.n_kv_heads / c.tp_size;
   e->group = c.n_heads / c.n_kv_heads;
@@ -536,8 +760,11 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   e->vocab_off = c.tp_rank * e->vocab_l;
   e->n_pages = (c.max_ctx + kPageTokens - 1) / kPageTokens;
   e->max_pos = e->n_pages * kPageTokens;
-  e->n_splits = c.attn_splits > 0 ? c.attn_splits : (e->sm_count + e->kv_heads_l - 1) / e->kv_heads_l;
-  if (e->n_splits > 16) e->n_splits = 16;
+  // split-KV factor: a constant of the engine (results are batch-invariant only for a fixed
+  // partition); 8 = the portable thread-block-cluster size -> one 64-key group per CTA up to
+  // ctx 512, two up to 1024
+  e->n_splits = c.attn_splits > 0 ? c.attn_splits : 8;
+  if (e->n_splits > 8) e->n_splits = 8;
   if (e->n_splits < 1) e->n_splits = 1;
 
   e->p_qkv = make_plan(e->q_rows + 2 * e->kv_rows, c.hidden, e->sm_count);
@@ -594,6 +821,10 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   TRY(alloc((void**)&e->part_ml, prow * 2 * 4));
   TRY(alloc((void**)&e->tickets, (size_t)e->kv_heads_l * 4));
   TRY(alloc((void**)&e->d_zero, 4));
+  TRY(alloc((void**)&e->grid_counter, 4));
+  if (getenv("LSK_MEGA_TIMELINE")) TRY(alloc((void**)&e->timeline, (4097 + 4 * 4096 * 4) * 8));
+  CU(cudaFuncSetAttribute(step_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  CU(cudaFuncSetAttribute(attn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   TRY(alloc((void**)&e->d_prompt, (size_t)e->max_pos * 4));
   TRY(alloc((void**)&e->state, sizeof(DevState)));
   TRY(alloc((void**)&e->gen_dev, sizeof(GenParams)));
@@ -625,6 +856,14 @@ void lsk_destroy(lsk_engine* e) {
   cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   if (e->comm) ncclCommDestroy(e->comm);
+  if (e->timeline && e->tl_rounds > 0) {
+    const char* names[8] = {"-", "attention", "small", "gemm_qkv", "gemm_resid(o+down)", "gemm_store", "gemm_silu", "gemm_lmhead"};
+    fprintf(stderr, "[lsk megakernel timeline] per round over %ld launches (stage = barrier-to-barrier on CTA 0):\n", e->tl_rounds);
+    for (int i = 1; i < 8; ++i) fprintf(stderr, "   %-20s %9.1f us\n", names[i], e->tl_ns[i] / e->tl_rounds / 1e3);
+    cudaFree(e->timeline);
+  }
+  for (auto& kv : e->programs) if (kv.second) cudaFree(kv.second);
+  if (e->grid_counter) cudaFree(e->grid_counter);
   for (auto& L : e->layers) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
   }
@@ -843,7 +1082,12 @@ int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
   if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context %d + %d exceeds max_ctx", e->host_len, d_req + 1);
   const int seq = ++e->seq;
   const long long key = ((long long)E << 20) | ((long long)d_req << 8) | (e->gen.sample ? 4 : 0) | 1;
-  TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
+  int served = 1;
+  if (e->use_mega && e->cfg.tp_size == 1 && !e->gen.sample) {
+    served = run_mega(e, key, [&]() { return enqueue_round(e, E, d_req, 0); });
+    if (served < 0) return served;
+  }
+  if (served == 1) TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
   (void)seq;
   copy_result(e, out);
   e->host_len = out->kv_len;
@@ -856,7 +1100,12 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
   if (e->host_len + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
   const int nl = (e->gen.exit_layer > 0 && e->gen.exit_layer <= e->cfg.n_layers) ? e->gen.exit_layer : e->cfg.n_layers;
   const long long key = ((long long)nl << 20) | (e->gen.sample ? 4 : 0) | 2;
-  TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
+  int served = 1;
+  if (e->use_mega && e->cfg.tp_size == 1 && !e->gen.sample) {
+    served = run_mega(e, key, [&]() { return enqueue_ar(e, nl, 0); });
+    if (served < 0) return served;
+  }
+  if (served == 1) TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
   *token_out = e->res_host->emitted_ids[0];
   e->host_len = e->res_host->kv_len;
   return LSK_OK;

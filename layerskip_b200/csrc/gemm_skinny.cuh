@@ -135,124 +135,131 @@ __host__ __device__ inline int gemm_x_stride_bytes(int kcols) {
   return ((2 * kcols + 127) / 128) * 128 + 64;   // == 64 (mod 128): conflict-free LDS.128
 }
 
-// shared-memory carve-up (host and device must agree)
-struct GemmSmem {
-  size_t ring, xs, red, stat, lg, bars, total;
+// shared-memory carve-up (host and device must agree).  Fixed part: mbarriers + ring; the
+// SCRATCH region behind it holds, per GEMM, the activation block, the partial-tile slots, RMS
+// statistics and the LM-head logits tile (and is reused by the attention teams of the step
+// megakernel).
+constexpr int kBarBytes = 1024;
+struct GemmScratch {
+  size_t xs, red, stat, lg, total;
 };
-__host__ __device__ inline GemmSmem gemm_smem_layout(int NT, int kc_cols, int tpp, int n_stages, int epi) {
-  GemmSmem L;
+__host__ __device__ inline GemmScratch gemm_scratch_layout(int NT, int kc_cols, int tpp, int epi) {
+  GemmScratch L;
   size_t off = 0;
-  L.ring = off; off += (size_t)n_stages * kStageBytes;
   L.xs = off;   off += (size_t)NT * 8 * gemm_x_stride_bytes(kc_cols);
   L.red = off;  off += (size_t)2 * tpp * kGemmWarps * NT * 128 * 4;
   L.stat = off; off += (size_t)(kGemmWarps + kEpiWarps + 1) * NT * 8 * 4;
   L.lg = off;   if (epi == EPI_LMHEAD) off += (size_t)NT * 8 * (tpp * 16) * 4;
-  off = (off + 15) & ~(size_t)15;
-  L.bars = off; off += (size_t)2 * kMaxStages * 8;
-  L.total = off;
+  L.total = (off + 127) & ~(size_t)127;
   return L;
 }
+__host__ __device__ inline size_t gemm_smem_total(int n_stages, size_t scratch_bytes) {
+  return (size_t)kBarBytes + (size_t)n_stages * kStageBytes + scratch_bytes;
+}
 
-// Kernel structure (one CTA per SM, persistent over tiles; 20 warps):
-//   warp 16      : PRODUCER — one elected lane walks this CTA's weight byte stream (tile after
-//                  tile, 16 KiB stages) and issues TMA bulk copies into the ring as slots free
-//                  up; it starts before the previous kernel has finished (weights never depend
-//                  on it) so the ring is full when the activations arrive
-//   warps 0..15  : CONSUMERS — warp w owns super-block w of every stage (an interleaved 16-way
-//                  K split): A fragments from the ring, B fragments from the resident
-//                  activations, mma.sync into per-tile accumulators; partial tiles are handed
-//                  to the epilogue warps through a double-buffered slot
-//   warps 17..19 : EPILOGUE — fixed-order reduction over the 16 K-slices + fused epilogue,
-//                  overlapped with the streaming of the next tile; at the end they pull the
-//                  NEXT kernel's first weights into L2.
-template <int NT, int PRO, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_skinny_kernel(const GemmArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int TPP = a.tiles_per_pass;
-  const int kc_cols = a.kc_sbs * 32;
-  const GemmSmem L = gemm_smem_layout(NT, kc_cols, TPP, a.n_stages, EPI);
-  const int XS = gemm_x_stride_bytes(kc_cols);
-  unsigned char* ring = smem + L.ring;
-  unsigned char* xs = smem + L.xs;
-  float* red = reinterpret_cast<float*>(smem + L.red);
-  const int kRedFloats = TPP * kGemmWarps * NT * 128;     // one buffer
-  float* stat = reinterpret_cast<float*>(smem + L.stat);
-  constexpr int kStatWarps = kGemmWarps + kEpiWarps;
-  float* lg = reinterpret_cast<float*>(smem + L.lg);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int n_slots = (a.n_tiles + TPP - 1) / TPP;        // a slot = TPP adjacent tiles
-  const int NS = a.n_stages;
-
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kGemmWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// Per-CTA pipeline context shared by the three warp roles.
+struct GemmCtx {
+  unsigned char* ring;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  unsigned char* scratch;
+  int NS;
+};
+__device__ __forceinline__ GemmCtx make_ctx(unsigned char* smem, int n_stages) {
+  GemmCtx c;
+  c.full_bar = reinterpret_cast<uint64_t*>(smem);
+  c.empty_bar = c.full_bar + kMaxStages;
+  c.ring = smem + kBarBytes;
+  c.scratch = c.ring + (size_t)n_stages * kStageBytes;
+  c.NS = n_stages;
+  return c;
+}
+__device__ __forceinline__ void ctx_init_barriers(const GemmCtx& c) {   // one thread
+  for (int s = 0; s < c.NS; ++s) {
+    mbar_init(&c.full_bar[s], 1);
+    mbar_init(&c.empty_bar[s], kGemmWarps);
   }
-  __syncthreads();
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
 
-  if (warp == kProducerWarp) {
-    // ================================================================== PRODUCER
-    pdl_launch_dependents();
-    if (lane == 0) {
-      uint32_t q = 0;
-      for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-        for (int kc = 0; kc < a.n_chunks; ++kc) {
-          const int sb_lo = kc * a.kc_sbs;
-          const int sb_hi = min(a.nsb, sb_lo + a.kc_sbs);
-          for (int j = 0; j < TPP; ++j) {
-            const int tile = slot * TPP + j;
-            if (tile >= a.n_tiles) break;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.W) +
-                                       ((size_t)tile * a.nsb + sb_lo) * 1024;
-            for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
-              const int cnt = min(kStageSbs, sb_hi - sb);
-              const int s = q % NS;
-              mbar_wait(&empty_bar[s], ((q / NS) & 1) ^ 1);
-              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cnt * 1024);
-              tma_bulk_g2s(ring + (size_t)s * kStageBytes, src + (size_t)(sb - sb_lo) * 1024,
-                           (uint32_t)cnt * 1024, &full_bar[s]);
-            }
-          }
+// ---------------------------------------------------------------------------------------------
+// PRODUCER (one lane): walk this CTA's weight byte stream, tile after tile in 16 KiB stages, and
+// issue TMA bulk copies into the ring as slots free up.  `q` counts stages over the kernel's
+// lifetime (it continues across the GEMM stages of the step megakernel).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemm_producer(const GemmArgs& a, const GemmCtx& c, uint32_t& q) {
+  const int TPP = a.tiles_per_pass;
+  const int n_slots = (a.n_tiles + TPP - 1) / TPP;
+  for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+    for (int kc = 0; kc < a.n_chunks; ++kc) {
+      const int sb_lo = kc * a.kc_sbs;
+      const int sb_hi = min(a.nsb, sb_lo + a.kc_sbs);
+      for (int j = 0; j < TPP; ++j) {
+        const int tile = slot * TPP + j;
+        if (tile >= a.n_tiles) break;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.W) +
+                                   ((size_t)tile * a.nsb + sb_lo) * 1024;
+        for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
+          const int cnt = min(kStageSbs, sb_hi - sb);
+          const int s = q % c.NS;
+          mbar_wait(&c.empty_bar[s], ((q / c.NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&c.full_bar[s], (uint32_t)cnt * 1024);
+          tma_bulk_g2s(c.ring + (size_t)s * kStageBytes, src + (size_t)(sb - sb_lo) * 1024,
+                       (uint32_t)cnt * 1024, &c.full_bar[s]);
         }
       }
     }
-    pdl_wait();   // completion stays transitive along the PDL chain
-    return;
   }
+}
 
-  pdl_launch_dependents();
-  pdl_wait();
-  const int wtid = (warp < kGemmWarps) ? tid : tid - 32;   // 0..607 over consumers + epilogue
-
-  // fills the resident activation chunk kc (bf16 source); callers sync around it
-  auto load_x_bf16 = [&](int kc, int ltid, int nthreads) {
-    const int col0 = kc * kc_cols;
-    const int cols = min(a.K - col0, kc_cols);
-    const int nvec = cols >> 3;                // uint4 (8 bf16) per row
-    const int zvec = kc_cols >> 3;
-    for (int m = 0; m < NT * 8; ++m) {
-      for (int idx = ltid; idx < zvec; idx += nthreads) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (m < a.M && idx < nvec)
-          v = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)m * a.xb_ld + col0 + idx * 8);
-        *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = v;
-      }
+// fills the resident activation chunk kc (bf16 source); callers sync around it
+template <int NT>
+__device__ __forceinline__ void gemm_load_x_bf16(const GemmArgs& a, unsigned char* xs, int XS,
+                                                 int kc_cols, int kc, int ltid, int nthreads) {
+  const int col0 = kc * kc_cols;
+  const int cols = min(a.K - col0, kc_cols);
+  const int nvec = cols >> 3;                // uint4 (8 bf16) per row
+  const int zvec = kc_cols >> 3;
+  for (int m = 0; m < NT * 8; ++m) {
+    for (int idx = ltid; idx < zvec; idx += nthreads) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (m < a.M && idx < nvec)
+        v = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)m * a.xb_ld + col0 + idx * 8);
+      *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = v;
     }
-  };
+  }
+}
 
-  // ------------------------------------------------------------------ prologue: x -> smem
+// ---------------------------------------------------------------------------------------------
+// PROLOGUE (consumer + epilogue warps, kWorkThreads): activations -> bf16 rows in scratch.
+// Ends with a BAR_WORK sync.
+// ---------------------------------------------------------------------------------------------
+// PRO_RMS: the norm weights are WEIGHTS — the stand-alone kernel loads them before the PDL
+// dependency resolves (gemm_preload_norm) and hands them in through `wreg`.
+__device__ __forceinline__ void gemm_preload_norm(const GemmArgs& a, int wtid, uint2 (&wreg)[4]) {
+  const int nvec = a.K >> 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = wtid + i * kWorkThreads;
+    wreg[i] = idx < nvec ? *reinterpret_cast<const uint2*>(a.norm_w + idx * 4) : make_uint2(0, 0);
+  }
+}
+
+template <int NT, int PRO>
+__device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& c, int epi,
+                                              int wtid, int swarp, int lane, const uint2 (&wreg)[4]) {
+  const int kc_cols = a.kc_sbs * 32;
+  const GemmScratch L = gemm_scratch_layout(NT, kc_cols, a.tiles_per_pass, epi);
+  const int XS = gemm_x_stride_bytes(kc_cols);
+  unsigned char* xs = c.scratch + L.xs;
+  float* stat = reinterpret_cast<float*>(c.scratch + L.stat);
+  constexpr int kStatWarps = kGemmWarps + kEpiWarps;
   if (PRO == PRO_RMS) {
     // Two passes over the (L1/L2-resident) residual rows: sum of squares, then normalise ->
     // bf16 (rounding point of a bf16 HF model: modeling_llama.py:52-70).  n_chunks == 1 here.
     const int nvec = a.K >> 2;  // float4 per row
-    const int swarp = (warp < kGemmWarps) ? warp : warp - 1;
+    // the norm weights arrive in registers (wreg) so that pass 2 only touches L1-resident rows:
+    // ONE dependent L2/HBM round trip instead of two
 #pragma unroll 1
     for (int m = 0; m < NT * 8; ++m) {
       float ss = 0.f;
@@ -278,13 +285,17 @@ gemm_skinny_kernel(const GemmArgs a) {
       if (m < a.M) {
         const float rstd = stat[kStatWarps * NT * 8 + m];
         const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)m * a.x_ld);
-        for (int idx = wtid; idx < nvec; idx += kWorkThreads) {
-          const float4 v = xr[idx];
-          const uint2 wv = *reinterpret_cast<const uint2*>(a.norm_w + idx * 4);
-          uint2 o;
-          o.x = pack_bf16x2(bf16_lo(wv.x) * (v.x * rstd), bf16_hi(wv.x) * (v.y * rstd));
-          o.y = pack_bf16x2(bf16_lo(wv.y) * (v.z * rstd), bf16_hi(wv.y) * (v.w * rstd));
-          *reinterpret_cast<uint2*>(xs + (size_t)m * XS + idx * 8) = o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = wtid + i * kWorkThreads;
+          if (idx < nvec) {
+            const float4 v = xr[idx];
+            const uint2 wv = wreg[i];
+            uint2 o;
+            o.x = pack_bf16x2(bf16_lo(wv.x) * (v.x * rstd), bf16_hi(wv.x) * (v.y * rstd));
+            o.y = pack_bf16x2(bf16_lo(wv.y) * (v.z * rstd), bf16_hi(wv.y) * (v.w * rstd));
+            *reinterpret_cast<uint2*>(xs + (size_t)m * XS + idx * 8) = o;
+          }
         }
       } else {
         for (int idx = wtid; idx < (kc_cols >> 3); idx += kWorkThreads)
@@ -292,219 +303,293 @@ gemm_skinny_kernel(const GemmArgs a) {
       }
     }
   } else if (a.n_chunks == 1) {
-    load_x_bf16(0, wtid, kWorkThreads);
+    gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, 0, wtid, kWorkThreads);
   }
   bar_sync(BAR_WORK, kWorkThreads);
+}
 
-  if (warp < kGemmWarps) {
-    // ================================================================== CONSUMER warps
-    const unsigned char* xlane = xs + (size_t)g * XS + t * 16;
-    uint32_t q = 0;
-    int it = 0;
-    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
-      float acc[kMaxTilesPerPass][NT][2][4];
+// ---------------------------------------------------------------------------------------------
+// CONSUMER warps (0..15): warp w owns super-block w of every stage (interleaved 16-way K split).
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c, int epi,
+                                             uint32_t& q, int tid, int warp, int lane) {
+  const int TPP = a.tiles_per_pass;
+  const int kc_cols = a.kc_sbs * 32;
+  const GemmScratch L = gemm_scratch_layout(NT, kc_cols, TPP, epi);
+  const int XS = gemm_x_stride_bytes(kc_cols);
+  unsigned char* xs = c.scratch + L.xs;
+  float* red = reinterpret_cast<float*>(c.scratch + L.red);
+  const int kRedFloats = TPP * kGemmWarps * NT * 128;     // one buffer
+  const int g = lane >> 2, t = lane & 3;
+  const int n_slots = (a.n_tiles + TPP - 1) / TPP;
+  const int NS = c.NS;
+  const unsigned char* xlane = xs + (size_t)g * XS + t * 16;
+  int it = 0;
+  for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
+    float acc[kMaxTilesPerPass][NT][2][4];
 #pragma unroll
-      for (int j = 0; j < kMaxTilesPerPass; ++j)
+    for (int j = 0; j < kMaxTilesPerPass; ++j)
 #pragma unroll
-        for (int n = 0; n < NT; ++n)
+      for (int n = 0; n < NT; ++n)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) acc[j][n][h][0] = acc[j][n][h][1] = acc[j][n][h][2] = acc[j][n][h][3] = 0.f;
+        for (int h = 0; h < 2; ++h) acc[j][n][h][0] = acc[j][n][h][1] = acc[j][n][h][2] = acc[j][n][h][3] = 0.f;
 
-      for (int kc = 0; kc < a.n_chunks; ++kc) {
-        if (a.n_chunks > 1) {            // swap the resident activation chunk
-          bar_sync(BAR_CONS, kConsumerThreads);
-          load_x_bf16(kc, tid, kConsumerThreads);
-          bar_sync(BAR_CONS, kConsumerThreads);
-        }
-        const int sb_lo = kc * a.kc_sbs;
-        const int sb_hi = min(a.nsb, sb_lo + a.kc_sbs);
-#pragma unroll
-        for (int j = 0; j < kMaxTilesPerPass; ++j) {
-          if (j < TPP && slot * TPP + j < a.n_tiles) {
-            for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
-              const int s = q % NS;
-              mbar_wait(&full_bar[s], (q / NS) & 1);
-              if (sb + warp < sb_hi) {
-                const unsigned char* ap = ring + (size_t)s * kStageBytes + warp * 1024 + lane * 16;
-                const uint4 a0 = *reinterpret_cast<const uint4*>(ap);
-                const uint4 a1 = *reinterpret_cast<const uint4*>(ap + 512);
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                  const uint4 b = *reinterpret_cast<const uint4*>(
-                      xlane + (size_t)n * 8 * XS + (size_t)(sb + warp - sb_lo) * 64);
-                  mma_bf16_16816(acc[j][n][0], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
-                  mma_bf16_16816(acc[j][n][1], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
-                }
-              }
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&empty_bar[s]);
-            }
-          }
-        }
+    for (int kc = 0; kc < a.n_chunks; ++kc) {
+      if (a.n_chunks > 1) {            // swap the resident activation chunk
+        bar_sync(BAR_CONS, kConsumerThreads);
+        gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, kc, tid, kConsumerThreads);
+        bar_sync(BAR_CONS, kConsumerThreads);
       }
-
-      const int buf = it & 1;
-      if (it >= 2) bar_sync(BAR_EMPTY0 + buf, kWorkThreads);   // epilogue released this slot
-      float* rbase = red + buf * kRedFloats;
+      const int sb_lo = kc * a.kc_sbs;
+      const int sb_hi = min(a.nsb, sb_lo + a.kc_sbs);
 #pragma unroll
       for (int j = 0; j < kMaxTilesPerPass; ++j) {
-        if (j < TPP) {
+        if (j < TPP && slot * TPP + j < a.n_tiles) {
+          for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
+            const int s = q % NS;
+            mbar_wait(&c.full_bar[s], (q / NS) & 1);
+            if (sb + warp < sb_hi) {
+              const unsigned char* ap = c.ring + (size_t)s * kStageBytes + warp * 1024 + lane * 16;
+              const uint4 a0 = *reinterpret_cast<const uint4*>(ap);
+              const uint4 a1 = *reinterpret_cast<const uint4*>(ap + 512);
 #pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            float* r = rbase + (((j * kGemmWarps + warp) * NT + n) * 16) * 8;
-            *reinterpret_cast<float2*>(r + g * 8 + 2 * t) =
-                make_float2(acc[j][n][0][0] + acc[j][n][1][0], acc[j][n][0][1] + acc[j][n][1][1]);
-            *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * t) =
-                make_float2(acc[j][n][0][2] + acc[j][n][1][2], acc[j][n][0][3] + acc[j][n][1][3]);
-          }
-        }
-      }
-      bar_arrive(BAR_FULL0 + buf, kWorkThreads);
-    }
-  } else {
-    // ================================================================== EPILOGUE warps
-    const int etid = tid - kConsumerThreads - 32;   // 0..95
-    const int ewarp = warp - kGemmWarps - 1;        // 0..2
-    constexpr int kRowsPerEwarp = (NT * 8 + kEpiWarps - 1) / kEpiWarps;
-    float best_v[kRowsPerEwarp];                    // LMHEAD: running arg-max, rows ewarp + 3*i
-    int best_i[kRowsPerEwarp];
-#pragma unroll
-    for (int i = 0; i < kRowsPerEwarp; ++i) { best_v[i] = -INFINITY; best_i[i] = 0x7fffffff; }
-
-    int it = 0;
-    for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const bool last = slot + gridDim.x >= n_slots;
-      if (last && a.next_bytes != 0) {
-        // HBM keeps streaming while this kernel drains and the next one ramps up
-        const unsigned long long share = ((a.next_bytes / gridDim.x) + 15) & ~15ull;
-        const unsigned long long lo = (unsigned long long)blockIdx.x * share;
-        if (lo < a.next_bytes) {
-          unsigned long long len = a.next_bytes - lo < share ? a.next_bytes - lo : share;
-          len &= ~15ull;
-          const unsigned long long per = ((len / kEpiThreads) + 15) & ~15ull;
-          const unsigned long long mylo = (unsigned long long)etid * per;
-          if (mylo < len && per > 0) {
-            const unsigned long long mylen = len - mylo < per ? len - mylo : per;
-            l2_prefetch_bulk(static_cast<const unsigned char*>(a.next_W) + lo + mylo, (uint32_t)mylen);
-          }
-        }
-      }
-      bar_sync(BAR_FULL0 + buf, kWorkThreads);
-      const float* rbase = red + buf * kRedFloats;
-      auto ksum = [&](int j, int n, int row, int tok) {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < kGemmWarps; ++k)
-          s += rbase[(((j * kGemmWarps + k) * NT + n) * 16 + row) * 8 + tok];
-        return s;
-      };
-
-      if (EPI == EPI_QKV || EPI == EPI_SILU) {
-        const int items = TPP * NT * 64;
-        for (int itx = etid; itx < items; itx += kEpiThreads) {
-          const int tok = itx & 7, r = (itx >> 3) & 7, n = (itx >> 6) % NT, j = (itx >> 6) / NT;
-          const int m = n * 8 + tok;
-          const int tile = slot * TPP + j;
-          if (m >= a.M || tile >= a.n_tiles) continue;
-          const float lo = ksum(j, n, r, tok), hi = ksum(j, n, r + 8, tok);
-          if (EPI == EPI_SILU) {
-            const float sg = lo / (1.f + __expf(-lo));
-            a.act[(size_t)m * a.act_ld + tile * 8 + r] = __float2bfloat16_rn(sg * hi);
-          } else {
-            const int pr = tile * 16;                     // first packed row of the tile
-            const int pos = *a.base_len + a.pos_off + m;
-            if (pr < a.q_rows + a.kv_rows) {              // q or k: rotary pair (d, d + 64)
-              const bool is_q = pr < a.q_rows;
-              const int rel = is_q ? pr : pr - a.q_rows;
-              const int head = rel >> 7, tt = (rel & 127) >> 4;
-              const int d = tt * 8 + r;
-              const float2 cs = a.rope[(size_t)pos * 64 + d];
-              const float o_lo = lo * cs.x - hi * cs.y;
-              const float o_hi = hi * cs.x + lo * cs.y;
-              if (is_q) {
-                __nv_bfloat16* qd = a.q_out + (size_t)m * a.q_ld + head * 128;
-                qd[d] = __float2bfloat16_rn(o_lo);
-                qd[d + 64] = __float2bfloat16_rn(o_hi);
-              } else {
-                const int page = a.page_table[pos >> 6];
-                __nv_bfloat16* kd = a.kpool +
-                    ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
-                kd[d] = __float2bfloat16_rn(o_lo);
-                kd[d + 64] = __float2bfloat16_rn(o_hi);
+              for (int n = 0; n < NT; ++n) {
+                const uint4 b = *reinterpret_cast<const uint4*>(
+                    xlane + (size_t)n * 8 * XS + (size_t)(sb + warp - sb_lo) * 64);
+                mma_bf16_16816(acc[j][n][0], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
+                mma_bf16_16816(acc[j][n][1], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
               }
-            } else {                                       // v: natural order, no rotation
-              const int rel = pr - a.q_rows - a.kv_rows;
-              const int head = rel >> 7, d0 = rel & 127;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c.empty_bar[s]);
+          }
+        }
+      }
+    }
+
+    const int buf = it & 1;
+    if (it >= 2) bar_sync(BAR_EMPTY0 + buf, kWorkThreads);   // epilogue released this slot
+    float* rbase = red + buf * kRedFloats;
+#pragma unroll
+    for (int j = 0; j < kMaxTilesPerPass; ++j) {
+      if (j < TPP) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          float* r = rbase + (((j * kGemmWarps + warp) * NT + n) * 16) * 8;
+          *reinterpret_cast<float2*>(r + g * 8 + 2 * t) =
+              make_float2(acc[j][n][0][0] + acc[j][n][1][0], acc[j][n][0][1] + acc[j][n][1][1]);
+          *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * t) =
+              make_float2(acc[j][n][0][2] + acc[j][n][1][2], acc[j][n][0][3] + acc[j][n][1][3]);
+        }
+      }
+    }
+    bar_arrive(BAR_FULL0 + buf, kWorkThreads);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPILOGUE warps (17..19): fixed-order reduction over the 16 K-slices + fused epilogue.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int EPI>
+__device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const GemmCtx& c, int etid,
+                                                   int ewarp, int lane) {
+  const int TPP = a.tiles_per_pass;
+  const int kc_cols = a.kc_sbs * 32;
+  const GemmScratch L = gemm_scratch_layout(NT, kc_cols, TPP, EPI);
+  float* red = reinterpret_cast<float*>(c.scratch + L.red);
+  float* lg = reinterpret_cast<float*>(c.scratch + L.lg);
+  const int kRedFloats = TPP * kGemmWarps * NT * 128;
+  const int n_slots = (a.n_tiles + TPP - 1) / TPP;
+  constexpr int kRowsPerEwarp = (NT * 8 + kEpiWarps - 1) / kEpiWarps;
+  float best_v[kRowsPerEwarp];                    // LMHEAD: running arg-max, rows ewarp + 3*i
+  int best_i[kRowsPerEwarp];
+#pragma unroll
+  for (int i = 0; i < kRowsPerEwarp; ++i) { best_v[i] = -INFINITY; best_i[i] = 0x7fffffff; }
+
+  int it = 0;
+  for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const bool last = slot + gridDim.x >= n_slots;
+    if (last && a.next_bytes != 0) {
+      // HBM keeps streaming while this kernel drains and the next one ramps up
+      const unsigned long long share = ((a.next_bytes / gridDim.x) + 15) & ~15ull;
+      const unsigned long long lo = (unsigned long long)blockIdx.x * share;
+      if (lo < a.next_bytes) {
+        unsigned long long len = a.next_bytes - lo < share ? a.next_bytes - lo : share;
+        len &= ~15ull;
+        const unsigned long long per = ((len / kEpiThreads) + 15) & ~15ull;
+        const unsigned long long mylo = (unsigned long long)etid * per;
+        if (mylo < len && per > 0) {
+          const unsigned long long mylen = len - mylo < per ? len - mylo : per;
+          l2_prefetch_bulk(static_cast<const unsigned char*>(a.next_W) + lo + mylo, (uint32_t)mylen);
+        }
+      }
+    }
+    bar_sync(BAR_FULL0 + buf, kWorkThreads);
+    const float* rbase = red + buf * kRedFloats;
+    auto ksum = [&](int j, int n, int row, int tok) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kGemmWarps; ++k)
+        s += rbase[(((j * kGemmWarps + k) * NT + n) * 16 + row) * 8 + tok];
+      return s;
+    };
+
+    if (EPI == EPI_QKV || EPI == EPI_SILU) {
+      const int items = TPP * NT * 64;
+      for (int itx = etid; itx < items; itx += kEpiThreads) {
+        const int tok = itx & 7, r = (itx >> 3) & 7, n = (itx >> 6) % NT, j = (itx >> 6) / NT;
+        const int m = n * 8 + tok;
+        const int tile = slot * TPP + j;
+        if (m >= a.M || tile >= a.n_tiles) continue;
+        const float lo = ksum(j, n, r, tok), hi = ksum(j, n, r + 8, tok);
+        if (EPI == EPI_SILU) {
+          const float sg = lo / (1.f + __expf(-lo));
+          a.act[(size_t)m * a.act_ld + tile * 8 + r] = __float2bfloat16_rn(sg * hi);
+        } else {
+          const int pr = tile * 16;                     // first packed row of the tile
+          const int pos = *a.base_len + a.pos_off + m;
+          if (pr < a.q_rows + a.kv_rows) {              // q or k: rotary pair (d, d + 64)
+            const bool is_q = pr < a.q_rows;
+            const int rel = is_q ? pr : pr - a.q_rows;
+            const int head = rel >> 7, tt = (rel & 127) >> 4;
+            const int d = tt * 8 + r;
+            const float2 cs = a.rope[(size_t)pos * 64 + d];
+            const float o_lo = lo * cs.x - hi * cs.y;
+            const float o_hi = hi * cs.x + lo * cs.y;
+            if (is_q) {
+              __nv_bfloat16* qd = a.q_out + (size_t)m * a.q_ld + head * 128;
+              qd[d] = __float2bfloat16_rn(o_lo);
+              qd[d + 64] = __float2bfloat16_rn(o_hi);
+            } else {
               const int page = a.page_table[pos >> 6];
-              __nv_bfloat16* vd = a.vpool +
+              __nv_bfloat16* kd = a.kpool +
                   ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
-              vd[d0 + r] = __float2bfloat16_rn(lo);
-              vd[d0 + r + 8] = __float2bfloat16_rn(hi);
+              kd[d] = __float2bfloat16_rn(o_lo);
+              kd[d + 64] = __float2bfloat16_rn(o_hi);
             }
+          } else {                                       // v: natural order, no rotation
+            const int rel = pr - a.q_rows - a.kv_rows;
+            const int head = rel >> 7, d0 = rel & 127;
+            const int page = a.page_table[pos >> 6];
+            __nv_bfloat16* vd = a.vpool +
+                ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
+            vd[d0 + r] = __float2bfloat16_rn(lo);
+            vd[d0 + r + 8] = __float2bfloat16_rn(hi);
           }
-        }
-      } else {
-        const int items = TPP * NT * 128;
-        for (int itx = etid; itx < items; itx += kEpiThreads) {
-          const int row = itx & 15, tok = (itx >> 4) & 7, n = (itx >> 7) % NT, j = (itx >> 7) / NT;
-          const int m = n * 8 + tok;
-          const int tile = slot * TPP + j;
-          if (tile >= a.n_tiles) continue;
-          const int orow = tile * 16 + row;
-          const float v = (m < a.M) ? ksum(j, n, row, tok) : 0.f;
-          if (EPI == EPI_RESID) {
-            if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] += v;
-          } else if (EPI == EPI_STORE) {
-            if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
-          } else {  // LMHEAD
-            if (m < a.M && a.logits != nullptr && orow < a.n_valid_rows)
-              a.logits[(size_t)m * a.logits_ld + orow] = v;
-            lg[m * (TPP * 16) + j * 16 + row] = v;
-          }
-        }
-        if (EPI == EPI_LMHEAD) {
-          bar_sync(BAR_EPI, kEpiThreads);
-#pragma unroll
-          for (int i = 0; i < kRowsPerEwarp; ++i) {
-            const int m = ewarp + i * kEpiWarps;
-            if (m < NT * 8 && m < a.M) {
-              float bv = -INFINITY;
-              int bi = 0x7fffffff;
-              for (int c = lane; c < TPP * 16; c += 32) {
-                const int orow = slot * TPP * 16 + c;
-                if (orow < a.n_valid_rows && orow < a.n_tiles * 16) {
-                  const float v = lg[m * (TPP * 16) + c];
-                  if (better(v, orow, bv, bi)) { bv = v; bi = orow; }
-                }
-              }
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-              }
-              if (better(bv, bi, best_v[i], best_i[i])) { best_v[i] = bv; best_i[i] = bi; }
-            }
-          }
-          bar_sync(BAR_EPI, kEpiThreads);   // lg is rewritten by the next slot
         }
       }
-      if (slot + 2 * gridDim.x < n_slots) bar_arrive(BAR_EMPTY0 + buf, kWorkThreads);
-    }
-
-    if (EPI == EPI_LMHEAD) {
-#pragma unroll
-      for (int i = 0; i < kRowsPerEwarp; ++i) {
-        const int m = ewarp + i * kEpiWarps;
-        if (m < NT * 8 && m < a.M && lane == 0) {
-          a.part_val[blockIdx.x * kMaxRows + m] = best_v[i];
-          a.part_idx[blockIdx.x * kMaxRows + m] =
-              (best_i[i] == 0x7fffffff) ? 0x7fffffff : best_i[i] + a.vocab_off;
+    } else {
+      const int items = TPP * NT * 128;
+      for (int itx = etid; itx < items; itx += kEpiThreads) {
+        const int row = itx & 15, tok = (itx >> 4) & 7, n = (itx >> 7) % NT, j = (itx >> 7) / NT;
+        const int m = n * 8 + tok;
+        const int tile = slot * TPP + j;
+        if (tile >= a.n_tiles) continue;
+        const int orow = tile * 16 + row;
+        const float v = (m < a.M) ? ksum(j, n, row, tok) : 0.f;
+        if (EPI == EPI_RESID) {
+          if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] += v;
+        } else if (EPI == EPI_STORE) {
+          if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
+        } else {  // LMHEAD
+          if (m < a.M && a.logits != nullptr && orow < a.n_valid_rows)
+            a.logits[(size_t)m * a.logits_ld + orow] = v;
+          lg[m * (TPP * 16) + j * 16 + row] = v;
         }
+      }
+      if (EPI == EPI_LMHEAD) {
+        bar_sync(BAR_EPI, kEpiThreads);
+#pragma unroll
+        for (int i = 0; i < kRowsPerEwarp; ++i) {
+          const int m = ewarp + i * kEpiWarps;
+          if (m < NT * 8 && m < a.M) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int cidx = lane; cidx < TPP * 16; cidx += 32) {
+              const int orow = slot * TPP * 16 + cidx;
+              if (orow < a.n_valid_rows && orow < a.n_tiles * 16) {
+                const float v = lg[m * (TPP * 16) + cidx];
+                if (better(v, orow, bv, bi)) { bv = v; bi = orow; }
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (better(bv, bi, best_v[i], best_i[i])) { best_v[i] = bv; best_i[i] = bi; }
+          }
+        }
+        bar_sync(BAR_EPI, kEpiThreads);   // lg is rewritten by the next slot
+      }
+    }
+    if (slot + 2 * gridDim.x < n_slots) bar_arrive(BAR_EMPTY0 + buf, kWorkThreads);
+  }
+
+  if (EPI == EPI_LMHEAD) {
+#pragma unroll
+    for (int i = 0; i < kRowsPerEwarp; ++i) {
+      const int m = ewarp + i * kEpiWarps;
+      if (m < NT * 8 && m < a.M && lane == 0) {
+        a.part_val[blockIdx.x * kMaxRows + m] = best_v[i];
+        a.part_idx[blockIdx.x * kMaxRows + m] =
+            (best_i[i] == 0x7fffffff) ? 0x7fffffff : best_i[i] + a.vocab_off;
       }
     }
   }
+}
+
+// Everything a non-producer thread does for one GEMM (prologue, then its role).
+template <int NT, int PRO, int EPI>
+__device__ __forceinline__ void gemm_work(const GemmArgs& a, const GemmCtx& c, uint32_t& q,
+                                          int tid, int warp, int lane,
+                                          unsigned long long* phase_clk = nullptr,
+                                          const uint2* pre_wreg = nullptr) {
+  const int wtid = (warp < kGemmWarps) ? tid : tid - 32;   // 0..607 over consumers + epilogue
+  const int swarp = (warp < kGemmWarps) ? warp : warp - 1;
+  uint2 wreg[4];
+  if (PRO == PRO_RMS) {
+    if (pre_wreg != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wreg[i] = pre_wreg[i];
+    } else {
+      gemm_preload_norm(a, wtid, wreg);
+    }
+  }
+  gemm_prologue<NT, PRO>(a, c, EPI, wtid, swarp, lane, wreg);
+  if (phase_clk != nullptr && wtid == 0) phase_clk[1] = clock64();      // debug: prologue done
+  if (warp < kGemmWarps) gemm_consume<NT>(a, c, EPI, q, tid, warp, lane);
+  else gemm_epilogue_role<NT, EPI>(a, c, tid - kConsumerThreads - 32, warp - kGemmWarps - 1, lane);
+  if (phase_clk != nullptr && wtid == 0) phase_clk[2] = clock64();      // debug: my tiles consumed
+}
+
+// Stand-alone kernel (one CTA per SM, persistent over tiles; 20 warps):
+//   warp 16      : PRODUCER (starts before the previous kernel has finished: PDL)
+//   warps 0..15  : CONSUMERS
+//   warps 17..19 : EPILOGUE (+ L2 prefetch of the NEXT kernel's first weights at the end)
+template <int NT, int PRO, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_skinny_kernel(const GemmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GemmCtx c = make_ctx(smem, a.n_stages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) ctx_init_barriers(c);
+  __syncthreads();
+  uint32_t q = 0;
+  if (warp == kProducerWarp) {
+    pdl_launch_dependents();
+    if (lane == 0) gemm_producer(a, c, q);
+    pdl_wait();   // completion stays transitive along the PDL chain
+    return;
+  }
+  pdl_launch_dependents();
+  uint2 wreg[4];
+  if (PRO == PRO_RMS) gemm_preload_norm(a, (warp < kGemmWarps) ? tid : tid - 32, wreg);
+  pdl_wait();
+  gemm_work<NT, PRO, EPI>(a, c, q, tid, warp, lane, nullptr, PRO == PRO_RMS ? wreg : nullptr);
 }
 
 }  // namespace lsk

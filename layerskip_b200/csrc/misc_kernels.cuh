@@ -172,6 +172,32 @@ __device__ __forceinline__ bool is_eos(const GenParams& gp, int tok) {
 // not exist": d_actual = index of first EOS + 1.  Rows past d_actual were computed but, the
 // attention being causal, cannot influence rows <= d_actual; their KV entries lie beyond the
 // committed length and are overwritten later.
+// thread-0 part of the greedy accept: compares drafts with the verifier's arg-maxes, commits.
+__device__ __forceinline__ void accept_commit(const int* s_ver, int d, DevState* __restrict__ st,
+                                              const GenParams& g, RoundResult* __restrict__ res,
+                                              int seq) {
+  int d_act = d;
+  for (int i = 0; i < d; ++i)
+    if (is_eos(g, st->tok[1 + i])) { d_act = i + 1; break; }
+  int n = 0;
+  while (n < d_act && st->tok[1 + n] == s_ver[n]) ++n;
+  res->n_drafted = d_act;
+  res->n_matches = n;
+  res->n_emitted = n + 1;
+  for (int i = 0; i < d_act; ++i) res->draft_ids[i] = st->tok[1 + i];
+  for (int i = 0; i <= d_act; ++i) res->verified_ids[i] = s_ver[i];
+  for (int i = 0; i < n; ++i) res->emitted_ids[i] = st->tok[1 + i];
+  res->emitted_ids[n] = s_ver[n];
+  for (int i = 0; i <= d; ++i) st->verified[i] = s_ver[i];
+  st->len += n + 1;
+  st->n_out += n + 1;
+  st->tok[0] = s_ver[n];
+  st->step_count += 1;
+  res->kv_len = st->len;
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(&res->seq) = seq;
+}
+
 __global__ void accept_greedy_kernel(const float* __restrict__ cand_val,
                                      const int* __restrict__ cand_idx, int n_cand, int d,
                                      DevState* __restrict__ st, const GenParams* __restrict__ gp,
@@ -185,32 +211,26 @@ __global__ void accept_greedy_kernel(const float* __restrict__ cand_val,
     if (lane == 0) s_ver[row] = tok;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const GenParams g = *gp;
-    int d_act = d;
-    for (int i = 0; i < d; ++i)
-      if (is_eos(g, st->tok[1 + i])) { d_act = i + 1; break; }
-    int n = 0;
-    while (n < d_act && st->tok[1 + n] == s_ver[n]) ++n;
-    res->n_drafted = d_act;
-    res->n_matches = n;
-    res->n_emitted = n + 1;
-    for (int i = 0; i < d_act; ++i) res->draft_ids[i] = st->tok[1 + i];
-    for (int i = 0; i <= d_act; ++i) res->verified_ids[i] = s_ver[i];
-    for (int i = 0; i < n; ++i) res->emitted_ids[i] = st->tok[1 + i];
-    res->emitted_ids[n] = s_ver[n];
-    for (int i = 0; i <= d; ++i) st->verified[i] = s_ver[i];
-    st->len += n + 1;
-    st->n_out += n + 1;
-    st->tok[0] = s_ver[n];
-    st->step_count += 1;
-    res->kv_len = st->len;
-    __threadfence_system();
-    *reinterpret_cast<volatile int*>(&res->seq) = seq;
-  }
+  if (threadIdx.x == 0) accept_commit(s_ver, d, st, *gp, res, seq);
 }
 
 // Autoregressive commit (autoregressive_generator.py:62-76): token = argmax(row 0).
+__device__ __forceinline__ void ar_commit(int tok, DevState* __restrict__ st,
+                                          RoundResult* __restrict__ res, int seq) {
+  st->tok[0] = tok;
+  st->len += 1;
+  st->n_out += 1;
+  st->step_count += 1;
+  res->n_drafted = 0;
+  res->n_matches = 0;
+  res->n_emitted = 1;
+  res->emitted_ids[0] = tok;
+  res->verified_ids[0] = tok;
+  res->kv_len = st->len;
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(&res->seq) = seq;
+}
+
 __global__ void ar_commit_kernel(const float* __restrict__ cand_val,
                                  const int* __restrict__ cand_idx, int n_cand,
                                  DevState* __restrict__ st, RoundResult* __restrict__ res,
@@ -219,20 +239,7 @@ __global__ void ar_commit_kernel(const float* __restrict__ cand_val,
   pdl_wait();
   if (threadIdx.x < 32) {
     const int tok = reduce_candidates(cand_val, cand_idx, n_cand, 0, threadIdx.x);
-    if (threadIdx.x == 0) {
-      st->tok[0] = tok;
-      st->len += 1;
-      st->n_out += 1;
-      st->step_count += 1;
-      res->n_drafted = 0;
-      res->n_matches = 0;
-      res->n_emitted = 1;
-      res->emitted_ids[0] = tok;
-      res->verified_ids[0] = tok;
-      res->kv_len = st->len;
-      __threadfence_system();
-      *reinterpret_cast<volatile int*>(&res->seq) = seq;
-    }
+    if (threadIdx.x == 0) ar_commit(tok, st, res, seq);
   }
 }
 

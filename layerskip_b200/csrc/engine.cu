@@ -127,7 +127,7 @@ struct lsk_engine {
   RoundResult* res_dev = nullptr;      // device alias of res_host
 
   GemmPlan p_qkv, p_o, p_gu, p_d, p_lm;
-  size_t l2_prefetch_bytes = 24u << 20;   // head of the NEXT kernel's weights pulled into L2
+  size_t l2_prefetch_bytes = 0;          // LSK_L2_PREFETCH_MB: head of the NEXT kernel's weights pulled into L2 (A/B: no gain, +11 % traffic -> off)
   int lm_cand = 0;                     // candidates produced by the LM head (its grid)
 
   cudaStream_t stream = nullptr;

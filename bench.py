@@ -486,6 +486,36 @@ def run_b200_arm(args):
                                                    "hbm_gbs": nb / (ms * 1e-3) / 1e9}
         except Exception as exc:  # pragma: no cover
             extra["autoregressive_same_engine"] = {"error": repr(exc)}
+        # acceptance-controlled legs: o_proj/down_proj of layers >= E damped by
+        # alpha; same architecture, prompts and settings, one 512-token generation each
+        sweep = []
+        for alpha in ([] if args.alpha != 1.0 else [0.3, 0.1, 0.03]):
+            try:
+                strat.engines.close()
+                m2 = SyntheticLlama(arch, seed=0, alpha=alpha, damp_from=args.exit_layer, device="cuda")
+                e2 = strat.engine_for(m2)
+                tot_ms, n_tok, mt, dr = 0.0, 0, 0, 0
+                for rep in range(2):        # rep 0 warms the graphs up
+                    e2.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
+                    e2.prefill(prompts[1])
+                    ms = e2.last_device_ms
+                    out = []
+                    while len(out) < args.max_steps:
+                        r = e2.round(min(args.num_speculations, args.max_steps - len(out) - 1))
+                        ms += e2.last_device_ms
+                        out += r.emitted
+                        if rep == 1:
+                            mt += r.n_matches
+                            dr += r.n_drafted
+                    if rep == 1:
+                        tot_ms, n_tok = ms, len(out)
+                sweep.append({"alpha": alpha, "acceptance_rate": mt / max(1, dr),
+                              "tokens_per_s": n_tok / (tot_ms * 1e-3)})
+                del m2
+            except Exception as exc:  # pragma: no cover
+                sweep.append({"alpha": alpha, "error": repr(exc)})
+        if sweep:
+            extra["acceptance_sweep"] = sweep
 
     if rank == 0:
         acc_mean = sum(accs) / max(1, len(accs))

@@ -217,7 +217,7 @@ struct GemmSched {
 };
 // fixed_ring == 0: stand-alone kernel, ring as deep as shared memory allows.
 // fixed_ring  > 0: megakernel stage, the scratch layout must fit behind a ring of that depth.
-static GemmSched plan_sched(int NT, int pro, int epi, const GemmPlan& p, int sm_count, int fixed_ring = 0) {
+static GemmSched plan_sched(int NT, int M, int pro, int epi, const GemmPlan& p, int sm_count, int fixed_ring = 0) {
   GemmSched best;
   for (int want = 1; want <= 16; ++want) {
     if (pro == PRO_RMS && want > 1) break;          // RMSNorm needs the whole row resident
@@ -225,7 +225,7 @@ static GemmSched plan_sched(int NT, int pro, int epi, const GemmPlan& p, int sm_
     if (want > 1) kc = (kc + kStageSbs - 1) / kStageSbs * kStageSbs;
     const int n_chunks = (p.nsb + kc - 1) / kc;
     const int tpp = n_chunks > 1 ? kMaxTilesPerPass : 1;
-    const GemmScratch L = gemm_scratch_layout(NT, kc * 32, tpp, epi);
+    const GemmScratch L = gemm_scratch_layout(NT, M, kc * 32, tpp, epi);
     const int st_hi = fixed_ring > 0 ? fixed_ring : kMaxStages;
     const int st_lo = fixed_ring > 0 ? fixed_ring : 2;
     for (int st = st_hi; st >= st_lo; --st) {
@@ -266,7 +266,7 @@ static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
-  const GemmSched sc = plan_sched(NT, PRO, EPI, p, e->sm_count);
+  const GemmSched sc = plan_sched(NT, a.M, PRO, EPI, p, e->sm_count);
   if (!sc.ok)
     return fail(LSK_ERR_INVALID, "skinny GEMM does not fit shared memory (K=%d, NT=%d)", p.K, NT);
   a.n_tiles = p.n_tiles;
@@ -276,6 +276,7 @@ static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
   a.n_chunks = sc.n_chunks;
   a.kc_sbs = sc.kc_sbs;
   a.n_stages = sc.n_stages;
+  a.xs_rows = a.M;
   CU(launch(e, kern, dim3(sc.grid), dim3(kGemmThreads), sc.smem, a));
   return LSK_OK;
 }
@@ -284,19 +285,19 @@ template <int PRO, int EPI>
 static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
   const int NT = a.M <= 8 ? 1 : 2;
   if (e->recording) {               // megakernel program: describe the stage instead of launching
-    const GemmSched sc = plan_sched(NT, PRO, EPI, p, e->sm_count, e->mega_ring);
+    const GemmSched sc = plan_sched(NT, a.M, PRO, EPI, p, e->sm_count, e->mega_ring);
     if (!sc.ok) { e->record_failed = true; return LSK_OK; }
     StageDesc d{};
     d.kind = ST_GEMM; d.nt = NT; d.pro = PRO; d.epi = EPI; d.barrier_before = 1;
     a.n_tiles = p.n_tiles; a.nsb = p.nsb; a.K = p.K;
-    a.tiles_per_pass = sc.tpp; a.n_chunks = sc.n_chunks; a.kc_sbs = sc.kc_sbs; a.n_stages = e->mega_ring;
+    a.tiles_per_pass = sc.tpp; a.n_chunks = sc.n_chunks; a.kc_sbs = sc.kc_sbs; a.n_stages = e->mega_ring; a.xs_rows = a.M;
     a.next_W = nullptr; a.next_bytes = 0;
     d.g = a;
     e->recording->push_back(d);
     return LSK_OK;
   }
   if (NT == 1) return launch_gemm_t<1, PRO, EPI>(e, p, a);
-  if (plan_sched(2, PRO, EPI, p, e->sm_count).ok) return launch_gemm_t<2, PRO, EPI>(e, p, a);
+  if (plan_sched(2, a.M, PRO, EPI, p, e->sm_count).ok) return launch_gemm_t<2, PRO, EPI>(e, p, a);
   return fail(LSK_ERR_INVALID, "%d token rows need the 16-row kernel, which does not fit next to K=%d "
               "(hidden sizes > 4096 support at most 8 rows, i.e. num_speculations <= 7)", a.M, p.K);
 }
@@ -774,7 +775,7 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   e->p_lm = make_plan(e->vocab_l_pad, c.hidden, e->sm_count);
   e->lm_cand = e->p_lm.n_tiles < e->sm_count ? e->p_lm.n_tiles : e->sm_count;
   if (const char* env = getenv("LSK_L2_PREFETCH_MB")) e->l2_prefetch_bytes = (size_t)atoi(env) << 20;
-  e->max_rows = plan_sched(2, PRO_RMS, EPI_QKV, e->p_qkv, e->sm_count).ok ? kMaxRows : 8;
+  e->max_rows = plan_sched(2, kMaxRows, PRO_RMS, EPI_QKV, e->p_qkv, e->sm_count).ok ? kMaxRows : 8;
 
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&e->ev0));

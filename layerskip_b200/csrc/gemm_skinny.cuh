@@ -94,6 +94,7 @@ struct GemmArgs {
   int n_chunks;         // K chunks whose activations are resident at a time
   int kc_sbs;           // super-blocks per chunk (multiple of kStageSbs unless n_chunks == 1)
   int n_stages;         // ring depth
+  int xs_rows;          // activation rows resident in shared memory (= M; absent rows read as 0)
   // ---- next kernel's weights: its head is pulled into L2 while this kernel drains
   const void* next_W;
   unsigned long long next_bytes;   // bytes worth prefetching (0 = none)
@@ -143,10 +144,10 @@ constexpr int kBarBytes = 1024;
 struct GemmScratch {
   size_t xs, red, stat, lg, total;
 };
-__host__ __device__ inline GemmScratch gemm_scratch_layout(int NT, int kc_cols, int tpp, int epi) {
+__host__ __device__ inline GemmScratch gemm_scratch_layout(int NT, int xs_rows, int kc_cols, int tpp, int epi) {
   GemmScratch L;
   size_t off = 0;
-  L.xs = off;   off += (size_t)NT * 8 * gemm_x_stride_bytes(kc_cols);
+  L.xs = off;   off += (size_t)xs_rows * gemm_x_stride_bytes(kc_cols);
   L.red = off;  off += (size_t)2 * tpp * kGemmWarps * NT * 128 * 4;
   L.stat = off; off += (size_t)(kGemmWarps + kEpiWarps + 1) * NT * 8 * 4;
   L.lg = off;   if (epi == EPI_LMHEAD) off += (size_t)NT * 8 * (tpp * 16) * 4;
@@ -220,7 +221,7 @@ __device__ __forceinline__ void gemm_load_x_bf16(const GemmArgs& a, unsigned cha
   const int cols = min(a.K - col0, kc_cols);
   const int nvec = cols >> 3;                // uint4 (8 bf16) per row
   const int zvec = kc_cols >> 3;
-  for (int m = 0; m < NT * 8; ++m) {
+  for (int m = 0; m < a.xs_rows; ++m) {
     for (int idx = ltid; idx < zvec; idx += nthreads) {
       uint4 v = make_uint4(0, 0, 0, 0);
       if (m < a.M && idx < nvec)
@@ -249,7 +250,7 @@ template <int NT, int PRO>
 __device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& c, int epi,
                                               int wtid, int swarp, int lane, const uint2 (&wreg)[4]) {
   const int kc_cols = a.kc_sbs * 32;
-  const GemmScratch L = gemm_scratch_layout(NT, kc_cols, a.tiles_per_pass, epi);
+  const GemmScratch L = gemm_scratch_layout(NT, a.xs_rows, kc_cols, a.tiles_per_pass, epi);
   const int XS = gemm_x_stride_bytes(kc_cols);
   unsigned char* xs = c.scratch + L.xs;
   float* stat = reinterpret_cast<float*>(c.scratch + L.stat);
@@ -281,7 +282,7 @@ __device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& 
     }
     bar_sync(BAR_WORK, kWorkThreads);
 #pragma unroll 1
-    for (int m = 0; m < NT * 8; ++m) {
+    for (int m = 0; m < a.xs_rows; ++m) {
       if (m < a.M) {
         const float rstd = stat[kStatWarps * NT * 8 + m];
         const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)m * a.x_ld);
@@ -316,7 +317,7 @@ __device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c
                                              uint32_t& q, int tid, int warp, int lane) {
   const int TPP = a.tiles_per_pass;
   const int kc_cols = a.kc_sbs * 32;
-  const GemmScratch L = gemm_scratch_layout(NT, kc_cols, TPP, epi);
+  const GemmScratch L = gemm_scratch_layout(NT, a.xs_rows, kc_cols, TPP, epi);
   const int XS = gemm_x_stride_bytes(kc_cols);
   unsigned char* xs = c.scratch + L.xs;
   float* red = reinterpret_cast<float*>(c.scratch + L.red);
@@ -325,6 +326,9 @@ __device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c
   const int n_slots = (a.n_tiles + TPP - 1) / TPP;
   const int NS = c.NS;
   const unsigned char* xlane = xs + (size_t)g * XS + t * 16;
+  bool row_ok[NT];                       // rows beyond xs_rows are not resident: B fragment = 0
+#pragma unroll
+  for (int n = 0; n < NT; ++n) row_ok[n] = (n * 8 + g) < a.xs_rows;
   int it = 0;
   for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
     float acc[kMaxTilesPerPass][NT][2][4];
@@ -355,8 +359,10 @@ __device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c
               const uint4 a1 = *reinterpret_cast<const uint4*>(ap + 512);
 #pragma unroll
               for (int n = 0; n < NT; ++n) {
-                const uint4 b = *reinterpret_cast<const uint4*>(
-                    xlane + (size_t)n * 8 * XS + (size_t)(sb + warp - sb_lo) * 64);
+                uint4 b = make_uint4(0, 0, 0, 0);
+                if (row_ok[n])
+                  b = *reinterpret_cast<const uint4*>(
+                      xlane + (size_t)n * 8 * XS + (size_t)(sb + warp - sb_lo) * 64);
                 mma_bf16_16816(acc[j][n][0], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
                 mma_bf16_16816(acc[j][n][1], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
               }
@@ -396,7 +402,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
                                                    int ewarp, int lane) {
   const int TPP = a.tiles_per_pass;
   const int kc_cols = a.kc_sbs * 32;
-  const GemmScratch L = gemm_scratch_layout(NT, kc_cols, TPP, EPI);
+  const GemmScratch L = gemm_scratch_layout(NT, a.xs_rows, kc_cols, TPP, EPI);
   float* red = reinterpret_cast<float*>(c.scratch + L.red);
   float* lg = reinterpret_cast<float*>(c.scratch + L.lg);
   const int kRedFloats = TPP * kGemmWarps * NT * 128;

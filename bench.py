@@ -266,7 +266,7 @@ def run_reference_arm(args):
                 cpu_steps = args.cpu_max_steps
             tokens, seconds, acc = cpu_reference_run(args, w, arch, prompts, max(1, args.steps), cpu_steps)
     except TimeoutError as exc:
-        print(json.dumps({"impl": "reference", "unavailable": f"CPU run did not finish: {exc}"}), flush=True)
+        emit(json.dumps({"impl": "reference", "unavailable": f"CPU run did not finish: {exc}"}))
         return
     value = tokens / seconds
     line = {
@@ -284,7 +284,7 @@ def run_reference_arm(args):
                                    f"prompt {args.prompt_len}, oracle port in torch {w_dtype} on {cores} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------
@@ -303,7 +303,6 @@ def run_b200_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: ONE JSON line
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
@@ -516,6 +515,32 @@ def run_b200_arm(args):
                 sweep.append({"alpha": alpha, "error": repr(exc)})
         if sweep:
             extra["acceptance_sweep"] = sweep
+        # the reference's DEFAULT decoding mode (sample=True, T=0.6, top_p=0.9; generator_base.py:39-42)
+        try:
+            eng_s = strat.engine_for(model) if args.alpha == 1.0 and not sweep else None
+            if eng_s is None:
+                strat.engines.close()
+                eng_s = strat.engine_for(model)
+            tot_ms, n_tok, mt, dr = 0.0, 0, 0, 0
+            for rep in range(2):
+                eng_s.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos,
+                            sample=True, temperature=0.6, top_k=0, top_p=0.9, seed=1234 + rep)
+                eng_s.prefill(prompts[2 % len(prompts)])
+                ms = eng_s.last_device_ms
+                out = []
+                while len(out) < args.max_steps:
+                    r = eng_s.round(min(args.num_speculations, args.max_steps - len(out) - 1))
+                    ms += eng_s.last_device_ms
+                    out += r.emitted
+                    if rep == 1:
+                        mt += r.n_matches
+                        dr += r.n_drafted
+                if rep == 1:
+                    tot_ms, n_tok = ms, len(out)
+            extra["sampling_T0.6_top_p0.9"] = {"acceptance_rate": mt / max(1, dr),
+                                               "tokens_per_s": n_tok / (tot_ms * 1e-3)}
+        except Exception as exc:  # pragma: no cover
+            extra["sampling_T0.6_top_p0.9"] = {"error": repr(exc)}
 
     if rank == 0:
         acc_mean = sum(accs) / max(1, len(accs))
@@ -537,14 +562,32 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu_baseline, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     strat.engines.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else any library
+    prints to fd 1 (NCCL's version banner, for one) was rerouted to stderr in main()."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "liblsk.so")
+LIB_PATH = os.environ.get("LSK_LIB") or os.path.join(PKG_DIR, "liblsk.so")   # LSK_LIB: tuning builds
 
 LSK_MAX_SPEC = 15
 LSK_MAX_EOS = 8

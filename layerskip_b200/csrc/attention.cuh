@@ -41,6 +41,7 @@ struct AttnArgs {
   float* part_ml;              // [kv][split][rows_pad][2]
   int rows_pad;                // group * 16 rounded up to 16
   int* tickets;                // [kv]
+  int n_pages;                 // entries in page_table
 };
 
 constexpr int kAttnTeamSmem = 2 * kKeyGroup * kKvRowBytes + 128;   // K/V staging + flag
@@ -64,6 +65,8 @@ __device__ __forceinline__ void attn_partial(const AttnArgs& a, int kvh, int spl
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
+  // the first page-table entry does not depend on the sequence length: fetch it alongside it
+  const int page_first = a.page_table[split < a.n_pages ? split : 0];
   const int base = *a.base_len + a.pos_off;          // position of token row 0
   const int n_keys = base + a.M;                      // keys visible to the last row
   const int n_kgroups = (n_keys + kKeyGroup - 1) / kKeyGroup;
@@ -99,7 +102,7 @@ __device__ __forceinline__ void attn_partial(const AttnArgs& a, int kvh, int spl
     for (int kg = split; kg < n_kgroups; kg += a.n_splits) {
       team_sync(bar_id);   // previous iteration's readers are done with ks / vs
       {
-        const int page = a.page_table[kg];   // kKeyGroup == kPageTokens
+        const int page = (kg == split) ? page_first : a.page_table[kg];   // kKeyGroup == kPageTokens
         const __nv_bfloat16* kp = a.kpool + (size_t)(page * a.n_kv_heads + kvh) * kPageTokens * kHeadDim;
         const __nv_bfloat16* vp = a.vpool + (size_t)(page * a.n_kv_heads + kvh) * kPageTokens * kHeadDim;
         for (int c = tid; c < kKeyGroup * 16; c += kAttnThreads) {
@@ -295,23 +298,40 @@ __device__ __forceinline__ void attn_team(const AttnArgs& a, int kvh, int split,
 template <typename FML, typename FO>
 __device__ __forceinline__ void merge_splits_write(const AttnArgs& a, int kvh, int row, int dseg,
                                                    FML ml, FO o) {
+  // all (m, l) pairs first, then the O segments in batches of independent loads: 1 + 4 remote
+  // latencies instead of a dependent chain of 2 x n_splits (same arithmetic, same order)
+  constexpr int kMaxSplits = 8;
+  float ms[kMaxSplits], ls[kMaxSplits];
+#pragma unroll
+  for (int s = 0; s < kMaxSplits; ++s) {
+    ms[s] = -INFINITY; ls[s] = 0.f;
+    if (s < a.n_splits) { const float* p = ml(s); ms[s] = p[0]; ls[s] = p[1]; }
+  }
   float mm = -INFINITY;
-  for (int s = 0; s < a.n_splits; ++s) mm = fmaxf(mm, ml(s)[0]);
+#pragma unroll
+  for (int s = 0; s < kMaxSplits; ++s) mm = fmaxf(mm, ms[s]);
+  float f[kMaxSplits];
   float ll = 0.f;
+#pragma unroll
+  for (int s = 0; s < kMaxSplits; ++s) {
+    f[s] = (ms[s] == -INFINITY) ? 0.f : __expf(ms[s] - mm);
+    if (s < a.n_splits) ll += ls[s] * f[s];
+  }
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int s = 0; s < a.n_splits; ++s) {
-    const float* mls = ml(s);
-    const float ms = mls[0];
-    const float f = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
-    ll += mls[1] * f;
-    const float4* po = reinterpret_cast<const float4*>(o(s));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 v = po[i];
-      acc[4 * i] += v.x * f; acc[4 * i + 1] += v.y * f;
-      acc[4 * i + 2] += v.z * f; acc[4 * i + 3] += v.w * f;
+  for (int i = 0; i < 4; ++i) {
+    float4 v[kMaxSplits];
+#pragma unroll
+    for (int s = 0; s < kMaxSplits; ++s)
+      v[s] = (s < a.n_splits) ? reinterpret_cast<const float4*>(o(s))[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < kMaxSplits; ++s) {
+      if (s < a.n_splits) {
+        acc[4 * i] += v[s].x * f[s]; acc[4 * i + 1] += v[s].y * f[s];
+        acc[4 * i + 2] += v[s].z * f[s]; acc[4 * i + 3] += v[s].w * f[s];
+      }
     }
   }
   const float inv = 1.f / ll;

@@ -339,7 +339,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.n_kv_heads = e->kv_heads_l; a.n_splits = e->n_splits;
     a.scale = 1.0f / sqrtf((float)c.head_dim);
     a.part_o = e->part_o; a.part_ml = e->part_ml; a.rows_pad = e->group * 16;
-    a.tickets = e->tickets;
+    a.tickets = e->tickets; a.n_pages = e->n_pages;
     if (e->recording) {
       StageDesc d{};
       d.kind = ST_ATTN; d.barrier_before = 1; d.a = a;
@@ -765,6 +765,7 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   // partition); 8 = the portable thread-block-cluster size -> one 64-key group per CTA up to
   // ctx 512, two up to 1024
   e->n_splits = c.attn_splits > 0 ? c.attn_splits : 8;
+  if (const char* env = getenv("LSK_ATTN_SPLITS")) e->n_splits = atoi(env);   // clamped to [1, 8] below
   if (e->n_splits > 8) e->n_splits = 8;
   if (e->n_splits < 1) e->n_splits = 1;
 

@@ -34,9 +34,12 @@ constexpr int kEpiThreads = kEpiWarps * 32;          // 96
 constexpr int kGemmThreads = kConsumerThreads + 32 + kEpiThreads;   // + 1 producer warp = 640
 constexpr int kWorkThreads = kConsumerThreads + kEpiThreads;        // everyone but the producer
 constexpr int kProducerWarp = kGemmWarps;            // warp 16
-constexpr int kStageSbs = 16;                        // super-blocks (1 KiB each) per ring stage
+#ifndef LSK_STAGE_SBS
+#define LSK_STAGE_SBS 16
+#endif
+constexpr int kStageSbs = LSK_STAGE_SBS;             // super-blocks (1 KiB each) per ring stage
 constexpr int kStageBytes = kStageSbs * 1024;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 128 / LSK_STAGE_SBS;      // ring capped at 128 KiB
 constexpr int kMaxTilesPerPass = 2;
 
 // named barriers (0 is __syncthreads)
@@ -353,18 +356,22 @@ __device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c
           for (int sb = sb_lo; sb < sb_hi; sb += kStageSbs, ++q) {
             const int s = q % NS;
             mbar_wait(&c.full_bar[s], (q / NS) & 1);
-            if (sb + warp < sb_hi) {
-              const unsigned char* ap = c.ring + (size_t)s * kStageBytes + warp * 1024 + lane * 16;
-              const uint4 a0 = *reinterpret_cast<const uint4*>(ap);
-              const uint4 a1 = *reinterpret_cast<const uint4*>(ap + 512);
 #pragma unroll
-              for (int n = 0; n < NT; ++n) {
-                uint4 b = make_uint4(0, 0, 0, 0);
-                if (row_ok[n])
-                  b = *reinterpret_cast<const uint4*>(
-                      xlane + (size_t)n * 8 * XS + (size_t)(sb + warp - sb_lo) * 64);
-                mma_bf16_16816(acc[j][n][0], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
-                mma_bf16_16816(acc[j][n][1], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
+            for (int w2 = 0; w2 < (kStageSbs + kGemmWarps - 1) / kGemmWarps; ++w2) {
+              const int wsb = warp + w2 * kGemmWarps;        // this warp's super-block(s) in the stage
+              if (wsb < kStageSbs && sb + wsb < sb_hi) {
+                const unsigned char* ap = c.ring + (size_t)s * kStageBytes + wsb * 1024 + lane * 16;
+                const uint4 a0 = *reinterpret_cast<const uint4*>(ap);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(ap + 512);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                  uint4 b = make_uint4(0, 0, 0, 0);
+                  if (row_ok[n])
+                    b = *reinterpret_cast<const uint4*>(
+                        xlane + (size_t)n * 8 * XS + (size_t)(sb + wsb - sb_lo) * 64);
+                  mma_bf16_16816(acc[j][n][0], a0.x, a0.y, a0.z, a0.w, b.x, b.y);
+                  mma_bf16_16816(acc[j][n][1], a1.x, a1.y, a1.z, a1.w, b.z, b.w);
+                }
               }
             }
             __syncwarp();
@@ -432,6 +439,22 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
         }
       }
     }
+    // EPI_RESID: fetch the old residual values of this slot BEFORE waiting for the tile, so the
+    // tail of the kernel has no dependent global round trip (each element has one owner thread)
+    constexpr int kMaxItems = (kMaxTilesPerPass * NT * 128 + kEpiThreads - 1) / kEpiThreads;
+    float old_resid[kMaxItems];
+    if (EPI == EPI_RESID) {
+#pragma unroll
+      for (int k = 0; k < kMaxItems; ++k) {
+        const int itx = etid + k * kEpiThreads;
+        old_resid[k] = 0.f;
+        if (itx < TPP * NT * 128) {
+          const int row = itx & 15, tok = (itx >> 4) & 7, n = (itx >> 7) % NT, j = (itx >> 7) / NT;
+          const int m = n * 8 + tok, tile = slot * TPP + j;
+          if (m < a.M && tile < a.n_tiles) old_resid[k] = a.out_f32[(size_t)m * a.out_ld + tile * 16 + row];
+        }
+      }
+    }
     bar_sync(BAR_FULL0 + buf, kWorkThreads);
     const float* rbase = red + buf * kRedFloats;
     auto ksum = [&](int j, int n, int row, int tok) {
@@ -488,7 +511,10 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
       }
     } else {
       const int items = TPP * NT * 128;
-      for (int itx = etid; itx < items; itx += kEpiThreads) {
+#pragma unroll
+      for (int k = 0; k < kMaxItems; ++k) {
+        const int itx = etid + k * kEpiThreads;
+        if (itx >= items) continue;
         const int row = itx & 15, tok = (itx >> 4) & 7, n = (itx >> 7) % NT, j = (itx >> 7) / NT;
         const int m = n * 8 + tok;
         const int tile = slot * TPP + j;
@@ -496,7 +522,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
         const int orow = tile * 16 + row;
         const float v = (m < a.M) ? ksum(j, n, row, tok) : 0.f;
         if (EPI == EPI_RESID) {
-          if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] += v;
+          if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = old_resid[k] + v;
         } else if (EPI == EPI_STORE) {
           if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
         } else {  // LMHEAD

@@ -76,7 +76,7 @@ struct LayerWeights {
 };
 
 struct GemmPlan {
-  int n_tiles = 0, nsb = 0, K = 0, ks_log2 = 0, grid = 0;
+  int n_tiles = 0, nsb = 0, K = 0;
 };
 
 struct lsk_engine {
@@ -204,7 +204,7 @@ static GemmPlan make_plan(int n_rows, int K, int sm_count) {
   p.n_tiles = n_rows / 16;
   p.K = K;
   p.nsb = K / 32;
-  p.grid = sm_count;      // upper bound; the schedule below trims it to the slot count
+  (void)sm_count;
   return p;
 }
 

@@ -47,24 +47,6 @@ __global__ void pack_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t 
   }
 }
 
-__global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld,
-                                 int64_t n_rows, int64_t n_cols, __nv_bfloat16* __restrict__ dst) {
-  const int64_t n = n_rows * n_cols;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = src[(i / n_cols) * src_ld + i % n_cols];
-}
-
-// (cos, sin)(pos * theta^(-2i/d)), fp32 like transformers modeling_llama.py:73-135
-__global__ void rope_table_kernel(float2* __restrict__ tab, int max_pos, float theta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= max_pos * 64) return;
-  const int pos = i >> 6, d = i & 63;
-  const float inv_freq = 1.0f / powf(theta, (float)(2 * d) / (float)kHeadDim);
-  const float ang = (float)pos * inv_freq;
-  tab[i] = make_float2(cosf(ang), sinf(ang));
-}
-
 // ---------------------------------------------------------------------------------------
 // embedding gather: hidden[row] = float(embed[token])   (llama_model_utils.py:182,242,310)
 // ---------------------------------------------------------------------------------------

@@ -173,6 +173,18 @@ int lsk_last_device_ms(const lsk_engine* e, float* ms_out);
 int lsk_profile_round(lsk_engine* e, int32_t d_req, lsk_round_out* out, float* class_ms,
                       int64_t* class_launches, float* total_ms);
 
+/* Host-side launch schedule of one weight-streaming GEMM (pure host logic; works without a GPU):
+ * how many activation columns are resident at a time, tiles accumulated side by side, TMA ring
+ * depth, grid.  pro: 0 RMSNorm prologue, 1 bf16 copy; epi: 0 qkv/rope, 1 residual add, 2 store,
+ * 3 silu*up, 4 lm-head arg-max. */
+typedef struct {
+  int32_t ok, nt, tiles_per_pass, n_chunks, chunk_cols, ring_stages, stage_bytes, grid, block;
+  int32_t n_tiles;
+  int64_t smem_bytes, smem_limit;
+} lsk_gemm_plan;
+int lsk_plan_gemm(int64_t n_rows, int64_t k, int32_t m, int32_t pro, int32_t epi, int32_t sm_count,
+                  lsk_gemm_plan* out);
+
 /* Stand-alone kernel entry points used by the micro-benchmarks and unit tests: run the skinny
  * GEMM (y[m, n] = x[m, k] . W[n, k]^T, fp32 out) on packed weights / the split-KV attention on
  * caller-provided device buffers. */

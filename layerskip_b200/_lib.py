@@ -62,6 +62,13 @@ class lsk_round_out(C.Structure):
                 ("verified_ids", C.c_int32 * (LSK_MAX_SPEC + 1))]
 
 
+class lsk_gemm_plan(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("nt", C.c_int32), ("tiles_per_pass", C.c_int32),
+                ("n_chunks", C.c_int32), ("chunk_cols", C.c_int32), ("ring_stages", C.c_int32),
+                ("stage_bytes", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32),
+                ("n_tiles", C.c_int32), ("smem_bytes", C.c_int64), ("smem_limit", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/lsk.h declares
 SIGNATURES = {
     "lsk_abi_version": (C.c_int, []),
@@ -87,6 +94,8 @@ SIGNATURES = {
     "lsk_profile_round": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(lsk_round_out),
                                     C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_float)]),
+    "lsk_plan_gemm": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.POINTER(lsk_gemm_plan)]),
     "lsk_test_pack": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "lsk_test_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),

@@ -1233,6 +1233,30 @@ int lsk_last_device_ms(const lsk_engine* e, float* out) {
   return LSK_OK;
 }
 
+// Host-side schedule of one skinny GEMM (no GPU needed): what the launcher would do for
+// y[m, n_rows] = x[m, K] . W^T with the given prologue / epilogue kinds on `sm_count` SMs.
+int lsk_plan_gemm(int64_t n_rows, int64_t K, int32_t m, int32_t pro, int32_t epi, int32_t sm_count,
+                  lsk_gemm_plan* out) {
+  if (!out || n_rows % 16 || K % 32 || m < 1 || m > kMaxRows || sm_count < 1)
+    return fail(LSK_ERR_INVALID, "bad plan query");
+  const GemmPlan p = make_plan((int)n_rows, (int)K, sm_count);
+  const int NT = m <= 8 ? 1 : 2;
+  const GemmSched sc = plan_sched(NT, m, pro, epi, p, sm_count);
+  out->ok = sc.ok ? 1 : 0;
+  out->nt = NT;
+  out->tiles_per_pass = sc.tpp;
+  out->n_chunks = sc.n_chunks;
+  out->chunk_cols = sc.kc_sbs * 32;
+  out->ring_stages = sc.n_stages;
+  out->stage_bytes = kStageBytes;
+  out->grid = sc.grid;
+  out->block = kGemmThreads;
+  out->smem_bytes = (int64_t)sc.smem;
+  out->smem_limit = kSmemMax;
+  out->n_tiles = p.n_tiles;
+  return LSK_OK;
+}
+
 // ---- stand-alone kernel entry points (unit tests / micro-benchmarks) ---------------------
 int lsk_test_pack(const void* w, int64_t n, int64_t k, void* packed) {
   if (!w || !packed || n % 16 || k % 32) return fail(LSK_ERR_INVALID, "need n %% 16 == 0 and k %% 32 == 0");

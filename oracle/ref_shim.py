@@ -92,6 +92,10 @@ def install() -> None:
         def legacy_forward(self, hidden_states, attention_mask=None, position_ids=None,
                            past_key_value=None, output_attentions=False, use_cache=False,
                            padding_mask=None, **kwargs):
+            if kwargs.get("position_embeddings") is not None or "past_key_values" in kwargs:
+                # native transformers-5 call (e.g. model(input_ids=...)): leave it untouched
+                return original_forward(self, hidden_states, attention_mask=attention_mask,
+                                        position_ids=position_ids, use_cache=use_cache, **kwargs)
             cfg = self.self_attn.config
             rope = rope_cache.get(id(cfg))
             if rope is None:

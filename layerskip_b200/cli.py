@@ -89,10 +89,18 @@ def load_model_and_tokenizer(args: Arguments, exit_layer: int):
         model = SyntheticLlama(arch, seed=int(margs.get("seed", 0)), alpha=float(margs.get("alpha", 1.0)),
                                damp_from=exit_layer if exit_layer > 0 else None)
         return model, IntegerTokenizer(arch.vocab), margs
-    import transformers
-    tok = transformers.AutoTokenizer.from_pretrained(args.model, use_fast=False)
-    model = transformers.AutoModelForCausalLM.from_pretrained(args.model, torch_dtype=torch.bfloat16)
-    return model.eval(), tok, margs
+    # local HF checkpoint directory: streamed shard by shard into the engine (checkpoint.py);
+    # the HF model object is never built, so host memory stays at one tensor
+    from .checkpoint import CheckpointLlama
+    model = CheckpointLlama(args.model)
+    has_tok = any(os.path.exists(os.path.join(args.model, f))
+                  for f in ("tokenizer.model", "tokenizer.json", "tokenizer_config.json"))
+    if has_tok:
+        import transformers
+        tok = transformers.AutoTokenizer.from_pretrained(args.model, use_fast=False)
+    else:
+        tok = IntegerTokenizer(model.arch.vocab)
+    return model, tok, margs
 
 
 def make_strategy(name: str, margs: Dict[str, Any]):

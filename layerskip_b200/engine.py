@@ -100,8 +100,9 @@ class Engine:
         self.load_weights(iter_state_dict(sd, self.device))
 
     def load_model(self, model) -> None:
-        """HF `LlamaForCausalLM` (any device / float dtype) or a `SyntheticLlama`."""
-        if isinstance(model, SyntheticLlama):
+        """HF `LlamaForCausalLM` (any device / float dtype), or a streaming source with
+        `iter_weights(device)` (`SyntheticLlama`, `checkpoint.CheckpointLlama`)."""
+        if hasattr(model, "iter_weights"):
             self.load_weights(model.iter_weights(self.device))
         else:
             self.load_state_dict(model.state_dict())

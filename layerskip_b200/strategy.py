@@ -33,7 +33,8 @@ class _EngineCache:
         hit = self._by_id.get(key)
         if hit is not None and hit[0]() is model:
             return hit[1]
-        arch = model.arch if isinstance(model, SyntheticLlama) else LlamaArch.from_hf_config(model.config)
+        arch = model.arch if isinstance(getattr(model, "arch", None), LlamaArch) \
+            else LlamaArch.from_hf_config(model.config)
         kw = dict(self.kwargs)
         group = kw.pop("process_group", None)
         eng = Engine(arch, **kw)

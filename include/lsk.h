@@ -37,6 +37,7 @@ typedef enum {
 #define LSK_FLAG_NO_PDL 2u       /* disable programmatic dependent launch                    */
 #define LSK_FLAG_NO_GRAPH 4u     /* launch kernels eagerly instead of replaying CUDA graphs  */
 #define LSK_FLAG_MEGAKERNEL 8u   /* opt in: ONE persistent cooperative kernel per round / AR step     */
+#define LSK_FLAG_TP_ONESHOT 16u  /* opt in (tp_size > 1): one-shot collectives over peer-mapped HBM instead of NCCL */
 
 /* Llama architecture + engine sizing.  Replaces what the reference reads off the HF model
  * object (`model.config`, generate.py:54-67). */

@@ -17,6 +17,7 @@ LSK_FLAG_KEEP_LOGITS = 1
 LSK_FLAG_NO_PDL = 2
 LSK_FLAG_NO_GRAPH = 4
 LSK_FLAG_MEGAKERNEL = 8
+LSK_FLAG_TP_ONESHOT = 16
 
 (LSK_W_EMBED, LSK_W_FINAL_NORM, LSK_W_LM_HEAD, LSK_W_LN1, LSK_W_Q, LSK_W_K, LSK_W_V, LSK_W_O,
  LSK_W_LN2, LSK_W_GATE, LSK_W_UP, LSK_W_DOWN) = range(12)

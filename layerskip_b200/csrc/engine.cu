@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm_skinny.cuh"
 #include "megakernel.cuh"
+#include "tp_peer.cuh"
 #include "misc_kernels.cuh"
 #include "sampling.cuh"
 
@@ -134,6 +135,12 @@ struct lsk_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<long long, cudaGraphExec_t> graphs;
   ncclComm_t comm = nullptr;
+  // one-shot collectives over peer-mapped HBM (tp_peer.cuh); opt-in, NCCL otherwise
+  bool want_peer = false, peer_ok = false;
+  PeerComm peer{};
+  void* peer_region = nullptr;           // this rank's peer-visible allocation
+  void* peer_opened[kMaxPeers] = {};     // IPC mappings of the other ranks' regions
+  int* peer_err_host = nullptr;          // mapped pinned: set by a kernel whose wait timed out
 
   lsk_generation gen{};
   bool began = false, prefilled = false;
@@ -302,6 +309,26 @@ static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
               "(hidden sizes > 4096 support at most 8 rows, i.e. num_speculations <= 7)", a.M, p.K);
 }
 
+// Tensor parallel: x[0..M) += sum over ranks of tp_buf (the fp32 partial of a row-parallel GEMM).
+// Default: NCCL all-reduce + residual add.  Opt-in (tp_peer.cuh): ONE kernel that pushes the
+// partial to every peer over NVLink, waits for theirs and adds the rank-ordered sum.
+static int emit_allreduce_resid(lsk_engine* e, float* x, int M) {
+  const lsk_config& c = e->cfg;
+  if (e->peer_ok) {
+    e->cur_class = CLS_COMM;
+    const int n4 = M * c.hidden / 4;
+    const int grid = (n4 + kArVecPerCta - 1) / kArVecPerCta;      // <= kMaxArCtas (hidden <= 8192)
+    CU(launch(e, tp_allreduce_resid_kernel, dim3(grid), dim3(kArThreads), 0, e->peer,
+              (const float*)e->tp_buf, x, n4));
+    return LSK_OK;
+  }
+  e->cur_class = CLS_COMM;
+  NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+  e->cur_class = CLS_MISC;
+  CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
+  return LSK_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // one decoder layer on hidden rows [row0, row0 + M) at positions *base_len + pos_off + i
 //   (HF LlamaDecoderLayer as called at llama_model_utils.py:193-201,253-261,354-362,375-383)
@@ -388,9 +415,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     } else {
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_o, a)));
-      NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
-      e->cur_class = CLS_MISC;
-      CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
+      TRY(emit_allreduce_resid(e, x, M));
     }
   }
   {  // RMSNorm -> gate/up -> SiLU * up
@@ -416,9 +441,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     } else {
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_d, a)));
-      NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
-      e->cur_class = CLS_MISC;
-      CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
+      TRY(emit_allreduce_resid(e, x, M));
     }
   }
   return LSK_OK;
@@ -507,7 +530,10 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
   a.next_bytes = after_W ? (after_bytes < e->l2_prefetch_bytes ? after_bytes : e->l2_prefetch_bytes) : 0;
   TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
   e->cur_class = CLS_MISC;
-  if (c.tp_size > 1) {
+  if (c.tp_size > 1 && e->peer_ok) {
+    CU(launch(e, tp_gather_best_kernel, dim3(1), dim3(256), 0, e->peer, (const float*)e->cand_val,
+              (const int*)e->cand_idx, e->lm_cand, M, e->gath_val, e->gath_idx));
+  } else if (c.tp_size > 1) {
     CU(launch(e, rank_best_kernel, dim3(1), dim3(256), 0, (const float*)e->cand_val,
               (const int*)e->cand_idx, e->lm_cand, M, e->rank_val, e->rank_idx));
     NC(ncclAllGather(e->rank_val, e->gath_val, kMaxRows, ncclFloat, e->comm, e->stream));
@@ -749,6 +775,8 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   e->keep_logits = (c.flags & LSK_FLAG_KEEP_LOGITS) != 0;
   e->use_mega = ((c.flags & LSK_FLAG_MEGAKERNEL) || getenv("LSK_MEGA")) && !getenv("LSK_NO_MEGA");
   e->attn_cluster = !getenv("LSK_NO_ATTN_CLUSTER");
+  e->want_peer = c.tp_size > 1 && ((c.flags & LSK_FLAG_TP_ONESHOT) ||
+                                   (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) != 0));
   if (const char* env = getenv("LSK_MEGA_RING")) { int v = atoi(env); if (v >= 3 && v <= kMaxStages) e->mega_ring = v; }
   e->heads_l = c.n_heads / c.tp_size;
   e->kv_heads_l = c.n_kv_heads / c.tp_size;
@@ -857,6 +885,9 @@ void lsk_destroy(lsk_engine* e) {
   if (!e) return;
   cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (void* p : e->peer_opened) if (p) cudaIpcCloseMemHandle(p);
+  if (e->peer_region) cudaFree(e->peer_region);
+  if (e->peer_err_host) cudaFreeHost(e->peer_err_host);
   if (e->comm) ncclCommDestroy(e->comm);
   if (e->timeline && e->tl_rounds > 0) {
     const char* names[8] = {"-", "attention", "small", "gemm_qkv", "gemm_resid(o+down)", "gemm_store", "gemm_silu", "gemm_lmhead"};
@@ -889,12 +920,66 @@ int lsk_comm_unique_id(uint8_t id_out[128]) {
   return LSK_OK;
 }
 
+// Map every rank's peer region into this process (CUDA IPC; the handles travel over the engine's
+// own NCCL communicator) and switch the TP collectives to the one-shot kernels of tp_peer.cuh.
+static int peer_setup(lsk_engine* e) {
+  const int tp = e->cfg.tp_size, rank = e->cfg.tp_rank;
+  if (tp > kMaxPeers) return fail(LSK_ERR_INVALID, "one-shot collectives support at most %d ranks", kMaxPeers);
+  const PeerRegionLayout L = peer_region_layout(tp, e->cfg.hidden);
+  {
+    cudaError_t er = cudaMalloc(&e->peer_region, L.total);
+    if (er != cudaSuccess) return fail(LSK_ERR_NOMEM, "cudaMalloc(peer region, %zu) failed: %s", L.total, cudaGetErrorString(er));
+  }
+  CU(cudaMemset(e->peer_region, 0, L.total));
+  CU(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mine;
+  CU(cudaIpcGetMemHandle(&mine, e->peer_region));
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  unsigned char* d_h = nullptr;
+  CU(cudaMalloc((void**)&d_h, hb * tp));
+  CU(cudaMemcpy(d_h + hb * rank, &mine, hb, cudaMemcpyHostToDevice));
+  NC(ncclAllGather(d_h + hb * rank, d_h, hb, ncclUint8, e->comm, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  std::vector<cudaIpcMemHandle_t> all(tp);
+  CU(cudaMemcpy(all.data(), d_h, hb * tp, cudaMemcpyDeviceToHost));
+  cudaFree(d_h);
+  for (int r = 0; r < tp; ++r) {
+    if (r == rank) { e->peer.base[r] = (unsigned char*)e->peer_region; continue; }
+    void* p = nullptr;
+    cudaError_t er = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (er != cudaSuccess)
+      return fail(LSK_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s (one-shot TP collectives need "
+                  "one process per GPU with peer access)", r, cudaGetErrorString(er));
+    e->peer_opened[r] = p;
+    e->peer.base[r] = (unsigned char*)p;
+  }
+  CU(cudaHostAlloc((void**)&e->peer_err_host, sizeof(int), cudaHostAllocMapped));
+  *e->peer_err_host = 0;
+  CU(cudaHostGetDevicePointer((void**)&e->peer.error, e->peer_err_host, 0));
+  e->peer.rank = rank;
+  e->peer.size = tp;
+  e->peer.hidden = e->cfg.hidden;
+  // nobody may push into a region before its owner has zeroed it: all did (they produced a handle),
+  // and this all-reduce keeps the ranks together until every mapping exists
+  NC(ncclAllReduce(e->tp_buf, e->tp_buf, 1, ncclFloat, ncclSum, e->comm, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->peer_ok = true;
+  return LSK_OK;
+}
+
+static int peer_check(lsk_engine* e) {
+  if (e->peer_err_host && *(volatile int*)e->peer_err_host)
+    return fail(LSK_ERR_NCCL, "one-shot TP collective timed out waiting for another rank");
+  return LSK_OK;
+}
+
 int lsk_comm_init(lsk_engine* e, const uint8_t id_in[128]) {
   if (!e) return fail(LSK_ERR_INVALID, "null engine");
   if (e->cfg.tp_size == 1) return LSK_OK;
   ncclUniqueId id;
   memcpy(&id, id_in, 128);
   NC(ncclCommInitRank(&e->comm, e->cfg.tp_size, id, e->cfg.tp_rank));
+  if (e->want_peer) TRY(peer_setup(e));
   return LSK_OK;
 }
 
@@ -1057,6 +1142,7 @@ int lsk_prefill(lsk_engine* e, const int32_t* ids, int32_t n) {
   CU(cudaEventRecord(e->ev1, e->stream));
   CU(cudaEventSynchronize(e->ev1));
   CU(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  TRY(peer_check(e));
   e->host_len = n - 1;
   e->prefilled = true;
   return LSK_OK;
@@ -1091,6 +1177,7 @@ int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
   }
   if (served == 1) TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
   (void)seq;
+  TRY(peer_check(e));
   copy_result(e, out);
   e->host_len = out->kv_len;
   return LSK_OK;
@@ -1108,6 +1195,7 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
     if (served < 0) return served;
   }
   if (served == 1) TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
+  TRY(peer_check(e));
   *token_out = e->res_host->emitted_ids[0];
   e->host_len = e->res_host->kv_len;
   return LSK_OK;

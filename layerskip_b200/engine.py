@@ -30,7 +30,7 @@ class Engine:
     def __init__(self, arch: LlamaArch, max_ctx: int = 4096, tp_rank: int = 0, tp_size: int = 1,
                  keep_logits: bool = False, use_pdl: bool = True, use_graph: bool = True,
                  attn_splits: int = 0, device: Optional[torch.device] = None,
-                 use_megakernel: bool = False):
+                 use_megakernel: bool = False, tp_oneshot: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("layerskip_b200 needs a CUDA device (B200); there is no CPU path")
         self._lib = _lib.load()
@@ -40,7 +40,8 @@ class Engine:
         self.tp_rank, self.tp_size = tp_rank, tp_size
         flags = (_lib.LSK_FLAG_KEEP_LOGITS if keep_logits else 0) | \
                 (0 if use_pdl else _lib.LSK_FLAG_NO_PDL) | (0 if use_graph else _lib.LSK_FLAG_NO_GRAPH) | \
-                (_lib.LSK_FLAG_MEGAKERNEL if use_megakernel else 0)
+                (_lib.LSK_FLAG_MEGAKERNEL if use_megakernel else 0) | \
+                (_lib.LSK_FLAG_TP_ONESHOT if tp_oneshot else 0)
         cfg = _lib.lsk_config(
             vocab=arch.vocab, hidden=arch.hidden, inter=arch.inter, n_layers=arch.layers,
             n_heads=arch.heads, n_kv_heads=arch.kv_heads, head_dim=arch.head_dim,

@@ -55,3 +55,14 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_flag_constants_match_the_header():
+    import re
+    from layerskip_b200 import _lib
+    text = open(os.path.join(os.path.dirname(__file__), "..", "include", "lsk.h")).read()
+    flags = dict(re.findall(r"#define (LSK_FLAG_\w+) (\d+)u", text))
+    assert set(flags) == {n for n in dir(_lib) if n.startswith("LSK_FLAG_")}
+    for name, value in flags.items():
+        assert getattr(_lib, name) == int(value), name
+    assert len(set(flags.values())) == len(flags)       # distinct bits

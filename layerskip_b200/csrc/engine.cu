@@ -108,6 +108,8 @@ struct lsk_engine {
   __nv_bfloat16* act = nullptr;        // [16][inter_l]
   float* tp_buf = nullptr;             // [16][hidden] row-parallel partial sums (TP)
   float* logits = nullptr;             // [16][vocab_l_pad] (optional)
+  float* logits_gath = nullptr;        // TP sampling: [tp][16][vocab_l_pad] all-gathered shards
+  float* logits_full = nullptr;        // TP sampling: [16][vocab] rows every rank samples from
   float* probs_d = nullptr;            // sampling: [16][vocab] warped draft distributions
   float* probs_v = nullptr;            // sampling: [16][vocab] warped verifier distributions
   float* samp_scratch = nullptr;       // sampling: [vocab] residual weights
@@ -467,6 +469,9 @@ static int emit_embed(lsk_engine* e, const int* ids, float* rows, int n_rows) {
 }
 static const float* cand_val_ptr(lsk_engine* e);
 static const int* cand_idx_ptr(lsk_engine* e);
+// what the sampling kernels read: the local logits, or under TP the gathered [16][vocab] rows
+static const float* samp_logits(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->logits_full : e->logits; }
+static int samp_ld(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->cfg.vocab : e->vocab_l_pad; }
 static int n_cand(lsk_engine* e);
 static int emit_finalize(lsk_engine* e, int slot, float* dst_row) {
   const lsk_config& c = e->cfg;
@@ -530,6 +535,15 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
   a.next_bytes = after_W ? (after_bytes < e->l2_prefetch_bytes ? after_bytes : e->l2_prefetch_bytes) : 0;
   TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
   e->cur_class = CLS_MISC;
+  if (c.tp_size > 1 && e->gen.sample) {
+    // every rank needs the whole distribution: all-gather the vocab shards of the M rows, lay them
+    // out as [M][vocab]; all ranks then run the same warp / Philox draw and stay in lockstep
+    e->cur_class = CLS_COMM;
+    NC(ncclAllGather(e->logits, e->logits_gath, (size_t)M * e->vocab_l_pad, ncclFloat, e->comm, e->stream));
+    CU(launch(e, tp_logits_rows_kernel, dim3(32, M), dim3(256), 0, (const float*)e->logits_gath, c.tp_size, M,
+              e->vocab_l, e->vocab_l_pad, e->logits_full, c.vocab));
+    e->cur_class = CLS_MISC;
+  }
   if (c.tp_size > 1 && e->peer_ok) {
     CU(launch(e, tp_gather_best_kernel, dim3(1), dim3(256), 0, e->peer, (const float*)e->cand_val,
               (const int*)e->cand_idx, e->lm_cand, M, e->gath_val, e->gath_idx));
@@ -572,8 +586,8 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
     } else {
       // decode_next_token sampling branch (llama_model_utils.py:123-131): keep the warped
       // distribution of draft i (needed by the rejection test), draw tok[i+1], embed it.
-      CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->logits,
-                e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
+      CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, samp_logits(e),
+                samp_ld(e), c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
                 e->probs_d + (size_t)i * c.vocab, &e->state->tok[1 + i], (int)RNG_DRAFT, i));
       CU(launch(e, embed_tokens_kernel, dim3(1), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
                 (const int*)&e->state->tok[1 + i], e->hidden + (size_t)(i + 1) * c.hidden, c.hidden));
@@ -592,8 +606,8 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   if (!e->gen.sample) {
     TRY(emit_accept(e, d, seq));
   } else {
-    CU(launch(e, warp_and_sample_kernel, dim3(d + 1), dim3(kSampleThreads), 0, (const float*)e->logits,
-              e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
+    CU(launch(e, warp_and_sample_kernel, dim3(d + 1), dim3(kSampleThreads), 0, samp_logits(e),
+              samp_ld(e), c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
               e->probs_v, &e->state->verified[0], (int)RNG_VERIFY, 0));
     CU(launch(e, accept_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->probs_d,
               (const float*)e->probs_v, c.vocab, d, e->state, (const GenParams*)e->gen_dev, e->res_dev,
@@ -617,8 +631,8 @@ static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
   if (!e->gen.sample) {
     TRY(emit_ar_commit(e, seq));
   } else {
-    CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->logits,
-              e->vocab_l_pad, c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
+    CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, samp_logits(e),
+              samp_ld(e), c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
               e->probs_v, &e->state->verified[0], (int)RNG_VERIFY, 0));
     CU(launch(e, ar_commit_sampled_kernel, dim3(1), dim3(32), 0, e->state, e->res_dev, seq));
   }
@@ -901,7 +915,7 @@ void lsk_destroy(lsk_engine* e) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
   }
   void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->kpool, e->vpool, e->page_table, e->rope,
-                  e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
+                  e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->logits_gath, e->logits_full, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
                   e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx, e->part_o,
                   e->part_ml, e->tickets, e->d_zero, e->d_prompt, e->state, e->gen_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -1089,7 +1103,6 @@ int lsk_begin(lsk_engine* e, const lsk_generation* gen) {
   if (gen->n_eos < 0 || gen->n_eos > LSK_MAX_EOS) return fail(LSK_ERR_INVALID, "n_eos out of range");
   if (gen->exit_layer > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "exit_layer > n_layers");
   if (gen->sample) {
-    if (e->cfg.tp_size > 1) return fail(LSK_ERR_INVALID, "sampling under tensor parallelism is not supported (vocab-sharded logits)");
     if (!(gen->temperature > 0.f)) return fail(LSK_ERR_INVALID, "temperature must be > 0");
     auto alloc0 = [&](float** p, size_t n) -> int {
       if (*p) return LSK_OK;
@@ -1101,6 +1114,10 @@ int lsk_begin(lsk_engine* e, const lsk_generation* gen) {
     TRY(alloc0(&e->probs_d, (size_t)kMaxRows * e->cfg.vocab));
     TRY(alloc0(&e->probs_v, (size_t)kMaxRows * e->cfg.vocab));
     TRY(alloc0(&e->samp_scratch, (size_t)e->cfg.vocab));
+    if (e->cfg.tp_size > 1) {
+      TRY(alloc0(&e->logits_gath, (size_t)e->cfg.tp_size * kMaxRows * e->vocab_l_pad));
+      TRY(alloc0(&e->logits_full, (size_t)kMaxRows * e->cfg.vocab));
+    }
   }
   e->gen = *gen;
   GenParams gp{};

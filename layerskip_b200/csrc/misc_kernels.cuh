@@ -251,6 +251,19 @@ __global__ void rank_best_kernel(const float* __restrict__ cand_val,
   }
 }
 
+// Tensor-parallel sampling: all-gathered vocab shards [tp][M][vl_pad] -> rows [M][vocab]
+// (vocab = tp * vl; the padding columns of every shard are dropped).
+__global__ void tp_logits_rows_kernel(const float* __restrict__ gath, int tp, int M, int vl,
+                                      int vl_pad, float* __restrict__ full, int ld) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < tp * vl; j += gridDim.x * blockDim.x) {
+    const int r = j / vl, c = j - r * vl;
+    full[(size_t)row * ld + j] = gath[((size_t)r * M + row) * vl_pad + c];
+  }
+}
+
 __global__ void residual_add_kernel(float* __restrict__ hidden, int ld,
                                     const float* __restrict__ delta, int delta_ld, int n_cols) {
   pdl_launch_dependents();

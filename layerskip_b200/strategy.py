@@ -26,6 +26,7 @@ class _EngineCache:
 
     def __init__(self, **engine_kwargs):
         self.kwargs = engine_kwargs
+        self.process_group = engine_kwargs.get("process_group")
         self._by_id: Dict[int, Tuple[Any, Engine]] = {}
 
     def get(self, model) -> Engine:
@@ -58,6 +59,19 @@ class _EngineCache:
         self._by_id.clear()
 
 
+def _generation_seed(cache: "_EngineCache", eng: Engine, sample: bool) -> int:
+    """The reference draws from torch's global generator; the engine's Philox streams are keyed
+    by its seed.  Under tensor parallelism every rank must draw the SAME tokens, so rank 0's seed
+    is broadcast (only when sampling: the greedy path needs no extra collective)."""
+    seed = int(torch.initial_seed()) & 0xFFFFFFFF
+    if sample and eng.tp_size > 1:
+        from .parallel_util import broadcast_bytes
+        raw = broadcast_bytes(seed.to_bytes(4, "little"), 4, src=0,
+                              group=cache.process_group, device=eng.device)
+        seed = int.from_bytes(raw, "little")
+    return seed
+
+
 def _reject_unsupported(logits_processors) -> None:
     if logits_processors:
         raise NotImplementedError(
@@ -83,7 +97,7 @@ class B200SelfSpeculativeGenerationStrategy(GenerationStrategy):
         eng = self.engines.get(model)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
-                  seed=int(torch.initial_seed()) & 0xFFFFFFFF)
+                  seed=_generation_seed(self.engines, eng, cfg.sample))
         eng.prefill(input_ids)
         output_ids: List[int] = []
         matches = drafted = 0
@@ -138,7 +152,7 @@ class B200AutoRegressiveGenerationStrategy(GenerationStrategy):
         eng = self.engines.get(model)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
-                  seed=int(torch.initial_seed()) & 0xFFFFFFFF)
+                  seed=_generation_seed(self.engines, eng, cfg.sample))
         eng.prefill(input_ids)
         output_ids: List[int] = []
         prev = input_ids[-1]

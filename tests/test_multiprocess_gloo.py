@@ -49,3 +49,33 @@ def test_world_size_2_plumbing():
     assert res[0][1] == firsts[0::2] and res[1][1] == firsts[1::2]      # disjoint, covering
     assert all(r[2] for r in res)                                          # same id bytes everywhere
     assert all(r[3] == 11.0 for r in res) and all(r[4] == 8.0 for r in res)
+
+
+def _seed_worker(rank, world, port, q):
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from layerskip_b200.strategy import _EngineCache, _generation_seed
+        torch.manual_seed(1000 + rank)                      # ranks disagree, like unseeded processes
+        eng = type("E", (), dict(tp_size=world, device=None))()
+        cache = _EngineCache(tp_size=world)
+        q.put((rank, _generation_seed(cache, eng, True), _generation_seed(cache, eng, False)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sampling_seed_is_rank_zeros_on_every_tp_rank():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seed_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == 1000                  # sampling: rank 0's seed everywhere
+    assert (res[0][2], res[1][2]) == (1000, 1001)          # greedy: no collective, local seed

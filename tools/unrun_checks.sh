@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 set -x
 # 1. checkpoint-fed engine == state-dict-fed engine (1 GPU)
 timeout 300 python -m pytest tests/test_gpu_zz_checkpoint.py -x -q 2>&1 | tail -5 | tee gpurun_out/unrun_checkpoint.log
-# 2. one-shot peer collectives == NCCL path, bit for bit at TP=2 (2 GPUs)
+# 2. one-shot peer collectives == NCCL path, bit for bit at TP=2; sampling under TP (2 GPUs)
 LSK_TEST_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_gpu_tp.py -x -q 2>&1 | tail -8 | tee gpurun_out/unrun_tp_oneshot.log
 # 3. what it buys: 13B at TP=2, NCCL vs one-shot (short runs)
 for mode in 0 1; do

@@ -767,6 +767,8 @@ extern "C" {
 int lsk_abi_version(void) { return LSK_ABI_VERSION; }
 const char* lsk_last_error(void) { return g_last_error.c_str(); }
 
+static int create_into(lsk_engine* e, const lsk_config& c);
+
 int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   if (!cfg || !out) return fail(LSK_ERR_INVALID, "null argument");
   const lsk_config& c = *cfg;
@@ -779,7 +781,20 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   if (c.vocab % c.tp_size) return fail(LSK_ERR_INVALID, "vocab must divide by tp_size");
   if (c.n_layers < 1 || c.max_ctx < 2) return fail(LSK_ERR_INVALID, "bad n_layers / max_ctx");
 
+  // everything that can fail half-way runs in create_into(); a failure releases what was built
   lsk_engine* e = new lsk_engine();
+  const int st = create_into(e, c);
+  if (st != LSK_OK) {
+    const std::string why = g_last_error;
+    lsk_destroy(e);
+    g_last_error = why;
+    return st;
+  }
+  *out = e;
+  return LSK_OK;
+}
+
+static int create_into(lsk_engine* e, const lsk_config& c) {
   e->cfg = c;
   int dev = 0;
   CU(cudaGetDevice(&dev));
@@ -891,13 +906,12 @@ int lsk_create(const lsk_config* cfg, lsk_engine** out) {
     CU(cudaMemcpyAsync(e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }
-  *out = e;
   return LSK_OK;
 }
 
 void lsk_destroy(lsk_engine* e) {
   if (!e) return;
-  cudaStreamSynchronize(e->stream);
+  if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (void* p : e->peer_opened) if (p) cudaIpcCloseMemHandle(p);
   if (e->peer_region) cudaFree(e->peer_region);
@@ -920,9 +934,10 @@ void lsk_destroy(lsk_engine* e) {
                   e->part_ml, e->tickets, e->d_zero, e->d_prompt, e->state, e->gen_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->res_host) cudaFreeHost(e->res_host);
-  cudaEventDestroy(e->ev0);
-  cudaEventDestroy(e->ev1);
-  cudaStreamDestroy(e->stream);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  cudaGetLastError();   // a half-built engine may have left a sticky-free error behind
   delete e;
 }
 

@@ -66,3 +66,37 @@ def test_flag_constants_match_the_header():
     for name, value in flags.items():
         assert getattr(_lib, name) == int(value), name
     assert len(set(flags.values())) == len(flags)       # distinct bits
+
+
+def test_create_fails_cleanly_without_a_gpu_and_validates_arguments():
+    """No compute: `lsk_create` must turn a missing device / bad config into an error code and a
+    message, never a crash or a half-built handle (a failed create releases what it allocated)."""
+    import ctypes as C
+    import torch
+    from layerskip_b200 import _lib
+    lib = _lib.load()
+
+    def cfg(**over):
+        base = dict(vocab=512, hidden=256, inter=704, n_layers=2, n_heads=2, n_kv_heads=2,
+                    head_dim=128, rms_eps=1e-5, rope_theta=1e4, max_ctx=128, tp_rank=0, tp_size=1,
+                    attn_splits=0, flags=0)
+        base.update(over)
+        return _lib.lsk_config(**base)
+
+    for bad, needle in ((dict(head_dim=64), "head_dim"), (dict(tp_rank=2, tp_size=2), "tp_rank"),
+                        (dict(n_heads=3), "heads"), (dict(hidden=8200), "hidden"),
+                        (dict(inter=700), "intermediate"), (dict(max_ctx=1), "max_ctx"),
+                        (dict(vocab=511, tp_size=2), "vocab")):
+        h = C.c_void_p()
+        c = cfg(**bad)
+        assert lib.lsk_create(C.byref(c), C.byref(h)) == -1, bad       # LSK_ERR_INVALID
+        assert needle in lib.lsk_last_error().decode(), bad
+        assert not h.value
+    assert lib.lsk_create(None, None) == -1
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        c = cfg()
+        assert lib.lsk_create(C.byref(c), C.byref(h)) == -2            # LSK_ERR_CUDA
+        assert "cuda" in lib.lsk_last_error().decode().lower()
+        assert not h.value
+    lib.lsk_destroy(None)                                              # tolerated

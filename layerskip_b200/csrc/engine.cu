@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -269,11 +270,15 @@ static GemmSched plan_sched(int NT, int M, int pro, int epi, const GemmPlan& p, 
 
 template <int NT, int PRO, int EPI>
 static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
-  static bool configured = false;
+  // the attribute is per DEVICE: one process may drive engines on several GPUs
+  static std::atomic<uint64_t> configured{0};
   auto kern = gemm_skinny_kernel<NT, PRO, EPI>;
-  if (!configured) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_relaxed) & bit)) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_relaxed);
   }
   const GemmSched sc = plan_sched(NT, a.M, PRO, EPI, p, e->sm_count);
   if (!sc.ok)

@@ -566,8 +566,10 @@ def run_b200_arm(args):
                                    f"exit_layer={args.exit_layer}, num_speculations={args.num_speculations}, "
                                    f"greedy, {args.prompt_len}-id synthetic prompts, {args.max_steps}-token continuations",
                        "parallelism": f"tp{tp}" if tp > 1 else f"replicas{world}",
-                       **({"tp_collectives": "peer-oneshot (csrc/tp_peer.cuh)"
-                           if os.environ.get("LSK_TP_ONESHOT", "0") not in ("", "0") else "nccl"}
+                       **({"tp_collectives": {"": "nccl", "0": "nccl", "2": "peer-oneshot, push fused into "
+                                              "the GEMM epilogue (csrc/tp_peer.cuh)"}.get(
+                                                  os.environ.get("LSK_TP_ONESHOT", "0"),
+                                                  "peer-oneshot (csrc/tp_peer.cuh)")}
                           if tp > 1 else {}),
                        "l2": "inputs_exceed_l2 (weights 13.5 GB >> 126 MB L2)",
                        "step": "one full generation (prefill + rounds)"},

@@ -140,6 +140,7 @@ struct lsk_engine {
   ncclComm_t comm = nullptr;
   // one-shot collectives over peer-mapped HBM (tp_peer.cuh); opt-in, NCCL otherwise
   bool want_peer = false, peer_ok = false;
+  int peer_mode = 1;                     // 1: push kernel after the GEMM; 2: push fused into the GEMM epilogue
   PeerComm peer{};
   void* peer_region = nullptr;           // this rank's peer-visible allocation
   void* peer_opened[kMaxPeers] = {};     // IPC mappings of the other ranks' regions
@@ -336,6 +337,36 @@ static int emit_allreduce_resid(lsk_engine* e, float* x, int M) {
   return LSK_OK;
 }
 
+// Fused variant (peer_mode 2): the row-parallel GEMM pushes its tiles to every rank from its
+// epilogue (gemm_skinny_push_kernel), a small kernel waits for all ranks' CTAs and adds the
+// rank-ordered sum to the residual rows.
+static int emit_gemm_push_resid(lsk_engine* e, const GemmPlan& p, GemmArgs a, float* x) {
+  const lsk_config& c = e->cfg;
+  const int NT = a.M <= 8 ? 1 : 2;
+  const GemmSched sc = plan_sched(NT, a.M, PRO_BF16, EPI_PUSH, p, e->sm_count);
+  if (!sc.ok) return fail(LSK_ERR_INVALID, "skinny GEMM does not fit shared memory (K=%d, NT=%d)", p.K, NT);
+  if (sc.grid > kMaxGemmCtas) return fail(LSK_ERR_INVALID, "GEMM grid %d exceeds the peer flag array", sc.grid);
+  a.n_tiles = p.n_tiles; a.nsb = p.nsb; a.K = p.K;
+  a.tiles_per_pass = sc.tpp; a.n_chunks = sc.n_chunks; a.kc_sbs = sc.kc_sbs; a.n_stages = sc.n_stages;
+  a.xs_rows = a.M;
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_relaxed) & bit)) {
+    CU(cudaFuncSetAttribute(gemm_skinny_push_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CU(cudaFuncSetAttribute(gemm_skinny_push_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured.fetch_or(bit, std::memory_order_relaxed);
+  }
+  if (NT == 1) CU(launch(e, gemm_skinny_push_kernel<1>, dim3(sc.grid), dim3(kGemmThreads), sc.smem, a, e->peer));
+  else CU(launch(e, gemm_skinny_push_kernel<2>, dim3(sc.grid), dim3(kGemmThreads), sc.smem, a, e->peer));
+  e->cur_class = CLS_COMM;
+  const int n4 = a.M * c.hidden / 4;
+  const int grid = (n4 + kArVecPerCta - 1) / kArVecPerCta;
+  CU(launch(e, tp_finish_resid_kernel, dim3(grid), dim3(kArThreads), 0, e->peer, x, n4, sc.grid));
+  return LSK_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // one decoder layer on hidden rows [row0, row0 + M) at positions *base_len + pos_off + i
 //   (HF LlamaDecoderLayer as called at llama_model_utils.py:193-201,253-261,354-362,375-383)
@@ -419,6 +450,8 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     if (!tp) {
       a.out_f32 = x; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_RESID>(e, e->p_o, a)));
+    } else if (e->peer_ok && e->peer_mode == 2) {
+      TRY(emit_gemm_push_resid(e, e->p_o, a, x));
     } else {
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_o, a)));
@@ -445,6 +478,8 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     if (!tp) {
       a.out_f32 = x; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_RESID>(e, e->p_d, a)));
+    } else if (e->peer_ok && e->peer_mode == 2) {
+      TRY(emit_gemm_push_resid(e, e->p_d, a, x));
     } else {
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_d, a)));
@@ -811,6 +846,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->attn_cluster = !getenv("LSK_NO_ATTN_CLUSTER");
   e->want_peer = c.tp_size > 1 && ((c.flags & LSK_FLAG_TP_ONESHOT) ||
                                    (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) != 0));
+  if (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) == 2) e->peer_mode = 2;
   if (const char* env = getenv("LSK_MEGA_RING")) { int v = atoi(env); if (v >= 3 && v <= kMaxStages) e->mega_ring = v; }
   e->heads_l = c.n_heads / c.tp_size;
   e->kv_heads_l = c.n_kv_heads / c.tp_size;

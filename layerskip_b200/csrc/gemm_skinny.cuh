@@ -21,11 +21,14 @@
 // the same row computed inside a verify block (m = D+1).
 #pragma once
 #include "common.cuh"
+#include "tp_peer.cuh"
 
 namespace lsk {
 
 enum { PRO_RMS = 0, PRO_BF16 = 1 };
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_STORE = 2, EPI_SILU = 3, EPI_LMHEAD = 4 };
+// EPI_PUSH (tensor parallel, opt-in): like EPI_STORE, but the fp32 tile goes straight into every
+// rank's peer-visible region over NVLink while the kernel is still streaming (tp_peer.cuh)
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_STORE = 2, EPI_SILU = 3, EPI_LMHEAD = 4, EPI_PUSH = 5 };
 
 constexpr int kGemmWarps = 16;                       // consumer warps (LDS + MMA)
 constexpr int kEpiWarps = 3;                         // reduction / epilogue warps
@@ -406,7 +409,8 @@ __device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c
 // ---------------------------------------------------------------------------------------------
 template <int NT, int EPI>
 __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const GemmCtx& c, int etid,
-                                                   int ewarp, int lane) {
+                                                   int ewarp, int lane,
+                                                   const PeerComm* pc = nullptr) {
   const int TPP = a.tiles_per_pass;
   const int kc_cols = a.kc_sbs * 32;
   const GemmScratch L = gemm_scratch_layout(NT, a.xs_rows, kc_cols, TPP, EPI);
@@ -419,6 +423,17 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
   int best_i[kRowsPerEwarp];
 #pragma unroll
   for (int i = 0; i < kRowsPerEwarp; ++i) { best_v[i] = -INFINITY; best_i[i] = 0x7fffffff; }
+
+  // EPI_PUSH: where this rank's slot lives inside every rank's region for the current instance
+  unsigned int push_epoch = 0;
+  size_t push_off = 0, push_ar = 0, push_flags = 0;
+  if (EPI == EPI_PUSH) {
+    const PeerRegionLayout PL = peer_region_layout(pc->size, pc->hidden);
+    push_epoch = *reinterpret_cast<volatile unsigned int*>(peer_base(*pc, pc->rank) + PL.local) + 1u;
+    push_off = ((size_t)(push_epoch & 1u) * pc->size + pc->rank) * kMaxRows * pc->hidden;   // floats
+    push_ar = PL.ar_data;
+    push_flags = PL.gemm_flags;
+  }
 
   int it = 0;
   for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x, ++it) {
@@ -525,6 +540,13 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
           if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = old_resid[k] + v;
         } else if (EPI == EPI_STORE) {
           if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
+        } else if (EPI == EPI_PUSH) {
+          if (m < a.M) {
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+              if (r < pc->size)
+                reinterpret_cast<float*>(pc->base[r] + push_ar)[push_off + (size_t)m * pc->hidden + orow] = v;
+          }
         } else {  // LMHEAD
           if (m < a.M && a.logits != nullptr && orow < a.n_valid_rows)
             a.logits[(size_t)m * a.logits_ld + orow] = v;
@@ -561,6 +583,16 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
     if (slot + 2 * gridDim.x < n_slots) bar_arrive(BAR_EMPTY0 + buf, kWorkThreads);
   }
 
+  if (EPI == EPI_PUSH) {
+    // all of this CTA's tiles are on their way: make them visible system-wide, then tell every
+    // rank (this one included) that CTA blockIdx.x of rank pc->rank is done with this instance
+    __threadfence_system();
+    bar_sync(BAR_EPI, kEpiThreads);
+    if (etid < pc->size)
+      st_release_sys(reinterpret_cast<unsigned int*>(peer_base(*pc, etid) + push_flags) +
+                         pc->rank * kMaxGemmCtas + blockIdx.x, push_epoch);
+  }
+
   if (EPI == EPI_LMHEAD) {
 #pragma unroll
     for (int i = 0; i < kRowsPerEwarp; ++i) {
@@ -579,7 +611,8 @@ template <int NT, int PRO, int EPI>
 __device__ __forceinline__ void gemm_work(const GemmArgs& a, const GemmCtx& c, uint32_t& q,
                                           int tid, int warp, int lane,
                                           unsigned long long* phase_clk = nullptr,
-                                          const uint2* pre_wreg = nullptr) {
+                                          const uint2* pre_wreg = nullptr,
+                                          const PeerComm* pc = nullptr) {
   const int wtid = (warp < kGemmWarps) ? tid : tid - 32;   // 0..607 over consumers + epilogue
   const int swarp = (warp < kGemmWarps) ? warp : warp - 1;
   uint2 wreg[4];
@@ -594,7 +627,7 @@ __device__ __forceinline__ void gemm_work(const GemmArgs& a, const GemmCtx& c, u
   gemm_prologue<NT, PRO>(a, c, EPI, wtid, swarp, lane, wreg);
   if (phase_clk != nullptr && wtid == 0) phase_clk[1] = clock64();      // debug: prologue done
   if (warp < kGemmWarps) gemm_consume<NT>(a, c, EPI, q, tid, warp, lane);
-  else gemm_epilogue_role<NT, EPI>(a, c, tid - kConsumerThreads - 32, warp - kGemmWarps - 1, lane);
+  else gemm_epilogue_role<NT, EPI>(a, c, tid - kConsumerThreads - 32, warp - kGemmWarps - 1, lane, pc);
   if (phase_clk != nullptr && wtid == 0) phase_clk[2] = clock64();      // debug: my tiles consumed
 }
 
@@ -622,6 +655,27 @@ gemm_skinny_kernel(const GemmArgs a) {
   if (PRO == PRO_RMS) gemm_preload_norm(a, (warp < kGemmWarps) ? tid : tid - 32, wreg);
   pdl_wait();
   gemm_work<NT, PRO, EPI>(a, c, q, tid, warp, lane, nullptr, PRO == PRO_RMS ? wreg : nullptr);
+}
+
+// Tensor-parallel row-parallel GEMM whose epilogue pushes its tiles to every rank (EPI_PUSH).
+template <int NT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_skinny_push_kernel(const GemmArgs a, const __grid_constant__ PeerComm pc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GemmCtx c = make_ctx(smem, a.n_stages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) ctx_init_barriers(c);
+  __syncthreads();
+  uint32_t q = 0;
+  if (warp == kProducerWarp) {
+    pdl_launch_dependents();
+    if (lane == 0) gemm_producer(a, c, q);
+    pdl_wait();
+    return;
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  gemm_work<NT, PRO_BF16, EPI_PUSH>(a, c, q, tid, warp, lane, nullptr, nullptr, &pc);
 }
 
 }  // namespace lsk

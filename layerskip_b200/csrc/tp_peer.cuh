@@ -35,6 +35,7 @@ namespace lsk {
 
 constexpr int kMaxPeers = 8;
 constexpr int kMaxArCtas = 64;
+constexpr int kMaxGemmCtas = 160;                       // >= SM count: one flag per GEMM CTA
 constexpr int kArThreads = 256;
 constexpr int kArVecPerCta = 512;                       // float4 elements per CTA slice
 constexpr long long kPeerTimeoutCycles = 4000000000LL;  // ~2 s at 1.9 GHz
@@ -45,6 +46,7 @@ struct PeerRegionLayout {
   size_t ar_flags;   // uint32 [tp][kMaxArCtas]
   size_t g_data;     // uint32 [2 parities][tp][32]   (16 fp32 values + 16 int32 indices)
   size_t g_flags;    // uint32 [tp]
+  size_t gemm_flags; // uint32 [tp][kMaxGemmCtas]  (fused mode: raised by the GEMM's epilogue)
   size_t local;      // owner only: uint32 ar_epoch, int32 ar_ticket, uint32 g_epoch
   size_t total;
 };
@@ -56,6 +58,7 @@ __host__ __device__ inline PeerRegionLayout peer_region_layout(int tp, int hidde
   L.ar_flags = take((size_t)tp * kMaxArCtas * 4);
   L.g_data = take((size_t)2 * tp * 32 * 4);
   L.g_flags = take((size_t)tp * 4);
+  L.gemm_flags = take((size_t)tp * kMaxGemmCtas * 4);
   L.local = take(16);
   L.total = off;
   return L;
@@ -148,6 +151,55 @@ tp_allreduce_resid_kernel(const PeerComm pc, const float* __restrict__ partial,
   }
 
   // 4. the last CTA to finish advances the epoch (every CTA has read it by then)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int t = atomicAdd(ticket_p, 1);
+    if (t == (int)gridDim.x - 1) {
+      *ticket_p = 0;
+      *epoch_p = epoch;
+      __threadfence();
+    }
+  }
+}
+
+// FUSED mode (LSK_TP_ONESHOT=2): the row-parallel GEMM's epilogue (gemm_skinny.cuh, EPI_PUSH) has
+// already written its output tiles into slot [parity][my rank] of EVERY rank's region (its own
+// included) while the kernel was still streaming weights, and each of its CTAs raised
+// gemm_flags[my rank][cta].  This kernel only waits for the n_src CTAs of every rank, adds the
+// partials in rank order and the residual, and advances the epoch.
+__global__ void __launch_bounds__(kArThreads)
+tp_finish_resid_kernel(const PeerComm pc, float* __restrict__ x, int n4, int n_src) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const PeerRegionLayout L = peer_region_layout(pc.size, pc.hidden);
+  unsigned char* mine = peer_base(pc, pc.rank);
+  volatile unsigned int* epoch_p = reinterpret_cast<volatile unsigned int*>(mine + L.local);
+  int* ticket_p = reinterpret_cast<int*>(mine + L.local + 4);
+  const unsigned int epoch = *epoch_p + 1u;
+  const size_t slot4 = (size_t)kMaxRows * pc.hidden / 4;
+  const size_t par4 = (size_t)(epoch & 1u) * pc.size * slot4;
+  const int tid = threadIdx.x, c = blockIdx.x;
+  const unsigned int* flags = reinterpret_cast<const unsigned int*>(mine + L.gemm_flags);
+  for (int k = tid; k < pc.size * n_src; k += kArThreads) {
+    const int r = k / n_src, cta = k - r * n_src;
+    if (!peer_wait(flags + r * kMaxGemmCtas + cta, epoch)) *reinterpret_cast<volatile int*>(pc.error) = 1;
+  }
+  __syncthreads();
+  const int i0 = c * kArVecPerCta;
+  const int i1 = (i0 + kArVecPerCta < n4) ? i0 + kArVecPerCta : n4;
+  const float4* recv = reinterpret_cast<const float4*>(mine + L.ar_data) + par4;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (int i = i0 + tid; i < i1; i += kArThreads) {
+    float4 acc = __ldcg(recv + i);
+    for (int r = 1; r < pc.size; ++r) {
+      const float4 v = __ldcg(recv + (size_t)r * slot4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4 h = x4[i];
+    h.x += acc.x; h.y += acc.y; h.z += acc.z; h.w += acc.w;
+    x4[i] = h;
+  }
   __syncthreads();
   if (tid == 0) {
     __threadfence();

@@ -32,8 +32,10 @@ def _worker(rank, world, port, case_names, q, oneshot=False):
         from tests import golden_util as gu
         from tests import parity_util as pu
         from tests.test_gpu_engine import _Model
+        if oneshot == 2:                                  # push fused into the GEMM epilogue
+            os.environ["LSK_TP_ONESHOT"] = "2"
         spec = B200SelfSpeculativeGenerationStrategy(max_ctx=512, tp_rank=rank, tp_size=world,
-                                                     tp_oneshot=oneshot)
+                                                     tp_oneshot=bool(oneshot))
         ar = B200AutoRegressiveGenerationStrategy(engine_cache=spec.engines)
         out = {}
         for name in case_names:
@@ -99,12 +101,13 @@ def test_oneshot_peer_collectives_equal_the_nccl_path():
     the whole token stream must be identical, not merely within the margin gate."""
     names = ["gqa128_a0.1", "mha128_a0.1"]
     nccl = _run(names, oneshot=False)
-    peer = _run(names, oneshot=True)
-    for name in names:
-        assert peer[0][name]["spec"] == peer[1][name]["spec"]
-        assert peer[0][name]["spec"] == nccl[0][name]["spec"]
-        assert peer[0][name]["ar"] == nccl[0][name]["ar"]
-        assert peer[0][name]["acc"] == nccl[0][name]["acc"]
+    for mode in (1, 2):                      # 1: push kernel after the GEMM, 2: push in its epilogue
+        peer = _run(names, oneshot=mode)
+        for name in names:
+            assert peer[0][name]["spec"] == peer[1][name]["spec"], mode
+            assert peer[0][name]["spec"] == nccl[0][name]["spec"], mode
+            assert peer[0][name]["ar"] == nccl[0][name]["ar"], mode
+            assert peer[0][name]["acc"] == nccl[0][name]["acc"], mode
 
 
 def _sample_worker(rank, world, port, q):

@@ -7,9 +7,9 @@ set -x
 # 1. checkpoint-fed engine == state-dict-fed engine (1 GPU)
 timeout 300 python -m pytest tests/test_gpu_zz_checkpoint.py -x -q 2>&1 | tail -5 | tee gpurun_out/unrun_checkpoint.log
 # 2. one-shot peer collectives == NCCL path, bit for bit at TP=2; sampling under TP (2 GPUs)
-LSK_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_tp.py -x -q 2>&1 | tail -8 | tee gpurun_out/unrun_tp_oneshot.log
+LSK_TEST_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_tp.py -x -q 2>&1 | tail -8 | tee gpurun_out/unrun_tp_oneshot.log
 # 3. what it buys: 13B at TP=2, NCCL vs one-shot (short runs)
-for mode in 0 1; do
+for mode in 0 1 2; do
   LSK_TP_ONESHOT=$mode timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
     --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --tp --arch llama2-13b \
     --steps 2 --warmup 3 --max-steps 128 --no-extra --no-cpu-baseline > gpurun_out/unrun_tp13b_oneshot$mode.json 2> gpurun_out/unrun_tp13b_oneshot$mode.err

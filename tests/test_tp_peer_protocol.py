@@ -125,3 +125,98 @@ def test_harness_catches_single_buffered_slots():
             caught = True
             break
     assert caught
+
+
+# ---- fused mode (LSK_TP_ONESHOT=2): the GEMM's CTAs push + flag, a finish kernel waits for all ----
+class FusedRegion(Region):
+    def __init__(self, tp, n):
+        super().__init__(tp, n)
+        self.gemm_flags = [[0] * MAX_CTAS for _ in range(tp)]
+
+
+def _gemm_cta(rank, cta, grid, regions, partial, n, jitter):
+    mine = regions[rank]
+    epoch = mine.epoch + 1
+    par = epoch & 1
+    jitter()
+    for i in range(cta, n, grid):                       # this CTA's tiles, strided like the kernel
+        for r in range(len(regions)):                   # every rank, this one included
+            regions[r].data[par][rank][i] = partial[i]
+    jitter()
+    for r in range(len(regions)):
+        regions[r].gemm_flags[rank][cta] = epoch
+
+
+def _finish_cta(rank, cta, grid, n_src, regions, x, n, jitter, errors):
+    tp = len(regions)
+    mine = regions[rank]
+    epoch = mine.epoch + 1
+    par = epoch & 1
+    deadline = time.time() + 20.0
+    for r in range(tp):
+        for c in range(n_src):
+            while mine.gemm_flags[r][c] - epoch < 0:
+                if time.time() > deadline:
+                    errors.append(f"rank {rank} finish cta {cta} timed out at epoch {epoch}")
+                    return
+                time.sleep(0)
+    jitter()
+    for i in range(cta * n // grid, (cta + 1) * n // grid):
+        acc = None
+        for r in range(tp):
+            v = mine.data[par][r][i]
+            acc = v if acc is None else acc + v
+        x[i] += acc
+    with mine.lock:
+        mine.ticket += 1
+        if mine.ticket == grid:
+            mine.ticket = 0
+            mine.epoch = epoch
+
+
+def _fused_rank(rank, regions, partials, x, gemm_grids, fin_grids, n, seed, errors):
+    rng = random.Random(seed)
+
+    def jitter():
+        if rng.random() < 0.3:
+            time.sleep(rng.random() * 0.002)
+
+    def run(target, grid, args):
+        threads = [threading.Thread(target=target, args=(rank, c, grid) + args) for c in range(grid)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+
+    for inst in range(len(gemm_grids)):
+        run(_gemm_cta, gemm_grids[inst], (regions, partials[inst][rank], n, jitter))
+        run(_finish_cta, fin_grids[inst], (gemm_grids[inst], regions, x, n, jitter, errors))
+        if errors:
+            return
+        if rng.random() < 0.2:
+            time.sleep(rng.random() * 0.004)
+
+
+@pytest.mark.parametrize("tp,seed", [(2, 5), (3, 6), (4, 7)])
+def test_fused_protocol_delivers_every_sum_to_every_rank(tp, seed):
+    n, n_inst = 12, 40
+    rng = random.Random(seed)
+    gemm_grids = [rng.choice([1, 2, 3, MAX_CTAS]) for _ in range(n_inst)]
+    fin_grids = [rng.choice([1, 2, 3]) for _ in range(n_inst)]
+    partials = [[[rng.randrange(1, 1000) * 1000 ** r for _ in range(n)] for r in range(tp)]
+                for _ in range(n_inst)]
+    regions = [FusedRegion(tp, n) for _ in range(tp)]
+    xs = [[0] * n for _ in range(tp)]
+    errors = []
+    threads = [threading.Thread(target=_fused_rank, args=(r, regions, partials, xs[r], gemm_grids,
+                                                          fin_grids, n, seed * 31 + r, errors))
+               for r in range(tp)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    want = [sum(partials[k][r][i] for k in range(n_inst) for r in range(tp)) for i in range(n)]
+    for r in range(tp):
+        assert xs[r] == want, f"rank {r}"
+        assert regions[r].epoch == n_inst

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <string>
@@ -140,6 +141,7 @@ struct lsk_engine {
   ncclComm_t comm = nullptr;
   // one-shot collectives over peer-mapped HBM (tp_peer.cuh); opt-in, NCCL otherwise
   bool want_peer = false, peer_ok = false;
+  unsigned ablate = 0;                   // LSK_ABLATE: timing-only diagnostics, kernel classes NOT launched
   int peer_mode = 1;                     // 1: push kernel after the GEMM; 2: push fused into the GEMM epilogue
   PeerComm peer{};
   void* peer_region = nullptr;           // this rank's peer-visible allocation
@@ -382,7 +384,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
   const size_t h2 = (size_t)c.hidden * 2;
   auto cap = [&](size_t bytes) { return bytes < e->l2_prefetch_bytes ? bytes : e->l2_prefetch_bytes; };
 
-  {  // RMSNorm -> QKV -> RoPE -> KV append
+  if (!(e->ablate & (1u << CLS_QKV))) {  // RMSNorm -> QKV -> RoPE -> KV append
     e->cur_class = CLS_QKV;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wqkv);
@@ -395,7 +397,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.next_W = L.wo; a.next_bytes = e->l2_prefetch_bytes ? (size_t)e->q_rows * h2 : 0;
     TRY((launch_gemm<PRO_RMS, EPI_QKV>(e, e->p_qkv, a)));
   }
-  {  // attention over the paged cache
+  if (!(e->ablate & (1u << CLS_ATTN))) {  // attention over the paged cache
     e->cur_class = CLS_ATTN;
     AttnArgs a{};
     a.q = e->qbuf; a.q_ld = e->q_rows; a.out = e->attn_out; a.out_ld = e->q_rows;
@@ -440,7 +442,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       CU(launch(e, attn_splitkv_kernel, dim3(e->kv_heads_l, e->n_splits), dim3(kAttnThreads), 0, a));
     }
   }
-  {  // O projection (+ residual, or all-reduce then residual under TP)
+  if (!(e->ablate & (1u << CLS_O))) {  // O projection (+ residual, or all-reduce then residual under TP)
     e->cur_class = CLS_O;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wo);
@@ -458,7 +460,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       TRY(emit_allreduce_resid(e, x, M));
     }
   }
-  {  // RMSNorm -> gate/up -> SiLU * up
+  if (!(e->ablate & (1u << CLS_GATEUP))) {  // RMSNorm -> gate/up -> SiLU * up
     e->cur_class = CLS_GATEUP;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wgu);
@@ -468,7 +470,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.next_W = L.wd; a.next_bytes = cap((size_t)e->inter_l * h2);
     TRY((launch_gemm<PRO_RMS, EPI_SILU>(e, e->p_gu, a)));
   }
-  {  // down projection (+ residual)
+  if (!(e->ablate & (1u << CLS_DOWN))) {  // down projection (+ residual)
     e->cur_class = CLS_DOWN;
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wd);
@@ -573,7 +575,7 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
   a.part_val = e->cand_val; a.part_idx = e->cand_idx;
   a.next_W = after_W;
   a.next_bytes = after_W ? (after_bytes < e->l2_prefetch_bytes ? after_bytes : e->l2_prefetch_bytes) : 0;
-  TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
+  if (!(e->ablate & (1u << CLS_LMHEAD))) TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
   e->cur_class = CLS_MISC;
   if (c.tp_size > 1 && e->gen.sample) {
     // every rank needs the whole distribution: all-gather the vocab shards of the M rows, lay them
@@ -847,6 +849,20 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->want_peer = c.tp_size > 1 && ((c.flags & LSK_FLAG_TP_ONESHOT) ||
                                    (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) != 0));
   if (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) == 2) e->peer_mode = 2;
+  if (const char* env = getenv("LSK_ABLATE")) {
+    // diagnostics only: the named kernel classes are not launched (results are garbage, the
+    // round keeps its shape) so that t(full) - t(ablated) gives a class's cost INSIDE the graph
+    static const char* names[] = {"qkv", "attn", "o", "gate_up", "down", "lm_head"};
+    std::string list(env);
+    for (size_t pos = 0; pos <= list.size();) {            // comma-separated, exact names
+      const size_t end = std::min(list.find(',', pos), list.size());
+      const std::string tok = list.substr(pos, end - pos);
+      for (int i = 0; i < 6; ++i)
+        if (tok == names[i]) e->ablate |= 1u << i;
+      pos = end + 1;
+    }
+    if (e->ablate) fprintf(stderr, "[lsk] LSK_ABLATE=%s: kernel classes skipped, outputs are NOT valid\n", env);
+  }
   if (const char* env = getenv("LSK_MEGA_RING")) { int v = atoi(env); if (v >= 3 && v <= kMaxStages) e->mega_ring = v; }
   e->heads_l = c.n_heads / c.tp_size;
   e->kv_heads_l = c.n_kv_heads / c.tp_size;

@@ -1,5 +1,9 @@
 """Tiny driver for ncu: a 7B-shaped engine, a short prompt, a few speculation rounds.
-   python tools/profile_round.py [arch] [rounds] [ctx]"""
+   python tools/profile_round.py [arch] [rounds] [ctx]
+
+Cost of a kernel class INSIDE the replayed graph (what eager per-class timing cannot give):
+   for c in "" qkv attn o gate_up down lm_head; do LSK_ABLATE=$c python tools/profile_round.py; done
+and subtract the round times (LSK_ABLATE skips the named classes; outputs are garbage)."""
 import os
 import sys
 

@@ -29,3 +29,25 @@ def test_sweep_flags_and_defaults(monkeypatch):
 def test_model_args_string_parser():
     assert cli.parse_model_args("a=1,b=true,c=x,d=0.5") == {"a": 1, "b": True, "c": "x", "d": 0.5}
     assert cli.parse_model_args(None) == {} and cli.parse_model_args("") == {}
+
+
+def test_model_flag_accepts_a_checkpoint_directory(tmp_path):
+    """`--model <dir>` (reference: generate.py:54-67 loads with from_pretrained) resolves to the
+    streaming checkpoint reader + the integer tokenizer when the directory has no tokenizer files;
+    nothing touches a GPU until an engine is built."""
+    import torch
+    from layerskip_b200.checkpoint import CheckpointLlama, expected_shapes, save_checkpoint
+    from layerskip_b200.synthetic import IntegerTokenizer
+    from layerskip_b200.weights import ARCHS
+    arch = ARCHS["tiny-mha"]
+    g = torch.Generator().manual_seed(0)
+    tensors = ((n, (torch.randn(s, generator=g) * 0.02).to(torch.bfloat16))
+               for n, s in expected_shapes(arch).items())
+    save_checkpoint(str(tmp_path), arch, tensors, max_shard_bytes=1 << 20)
+    model, tok, margs = cli.load_model_and_tokenizer(
+        cli.Arguments(model=str(tmp_path), model_args="max_ctx=256"), exit_layer=2)
+    assert isinstance(model, CheckpointLlama) and model.arch == arch
+    assert isinstance(tok, IntegerTokenizer) and margs == {"max_ctx": 256}
+    assert model.config.num_hidden_layers == arch.layers       # what the strategies read
+    syn, tok2, _ = cli.load_model_and_tokenizer(cli.Arguments(model="synthetic:tiny-mha"), exit_layer=2)
+    assert syn.arch == arch and isinstance(tok2, IntegerTokenizer)

@@ -72,6 +72,17 @@ def _generation_seed(cache: "_EngineCache", eng: Engine, sample: bool) -> int:
     return seed
 
 
+def _check_context(eng, n_prompt: int, cfg: GenerationConfig) -> None:
+    """The KV pool is sized once (`max_ctx`): fail before the first kernel rather than mid-way.
+    The last round / step touches position n_prompt + max_steps (engine.cu: lsk_round, lsk_ar_step)."""
+    max_ctx = getattr(eng, "max_ctx", None)
+    need = n_prompt + cfg.max_steps + 1
+    if max_ctx is not None and need > max_ctx:
+        raise ValueError(f"prompt ({n_prompt}) + max_steps ({cfg.max_steps}) needs {need} KV positions but "
+                         f"the engine was built with max_ctx={max_ctx}; construct the strategy with a "
+                         "larger max_ctx")
+
+
 def _reject_unsupported(logits_processors) -> None:
     if logits_processors:
         raise NotImplementedError(
@@ -95,6 +106,7 @@ class B200SelfSpeculativeGenerationStrategy(GenerationStrategy):
         _reject_unsupported(logits_processors)
         cfg = generation_config
         eng = self.engines.get(model)
+        _check_context(eng, len(input_ids), cfg)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
                   seed=_generation_seed(self.engines, eng, cfg.sample))
@@ -150,6 +162,7 @@ class B200AutoRegressiveGenerationStrategy(GenerationStrategy):
         _reject_unsupported(logits_processors)
         cfg = generation_config
         eng = self.engines.get(model)
+        _check_context(eng, len(input_ids), cfg)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
                   seed=_generation_seed(self.engines, eng, cfg.sample))

@@ -162,3 +162,13 @@ def test_weight_name_classification_and_arch_table():
     assert ARCHS["llama2-70b"].kv_heads == 8 and ARCHS["llama3-8b"].vocab == 128256
     prompts = synthetic_prompts(32000, 8, 128)
     assert len(prompts) == 8 and all(len(p) == 128 and 3 <= min(p) and max(p) <= 31998 for p in prompts)
+
+
+def test_context_overflow_is_reported_before_any_kernel_runs():
+    from layerskip_b200.plugin import GenerationConfig
+    from layerskip_b200.strategy import _check_context
+    eng = type("E", (), dict(max_ctx=256))()
+    _check_context(eng, 100, GenerationConfig(max_steps=155))                 # 100 + 155 + 1 == 256
+    with pytest.raises(ValueError, match="max_ctx=256"):
+        _check_context(eng, 100, GenerationConfig(max_steps=156))
+    _check_context(object(), 10 ** 6, GenerationConfig(max_steps=512))        # engines without the attribute

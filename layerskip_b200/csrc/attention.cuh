@@ -369,6 +369,57 @@ attn_cluster_kernel(const AttnArgs a) {
   cluster.sync();      // nobody leaves while a peer may still read its partials
 }
 
+// Push variant of the cluster kernel (opt-in, LSK_ATTN_PUSH=1).  Same partials, same merge
+// arithmetic in the same order (merge_splits_write), but the exchange is turned around: instead of
+// every merging thread PULLING 1 + 4 dependent remote reads out of its peers' shared memory and
+// the cluster synchronising twice (once before the reads, once so nobody exits while being read),
+// every CTA PUSHES the slices of its partial to the CTA that will merge them (fire-and-forget
+// distributed-shared-memory stores), ONE cluster barrier publishes them, and the merge reads local
+// shared memory only; nobody touches a peer afterwards, so a CTA may exit right after its merge.
+// Items (row, 16-dim segment) are dealt round-robin over the cluster: item -> CTA item % n_splits.
+constexpr int kInboxStride = 20;    // floats per (split, item): 16 of O, m, l, 2 pad (16 B aligned)
+
+__host__ __device__ inline size_t attn_push_smem_bytes(int rows_pad) {
+  return (size_t)kAttnTeamSmem + (size_t)rows_pad * (kHeadDim + 2) * 4 + ((size_t)rows_pad * 8 + 8) * kInboxStride * 4;   // + 8: cap is rounded up per CTA
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+attn_cluster_push_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  float* po = reinterpret_cast<float*>(dsm + kAttnTeamSmem);
+  float* pml = po + (size_t)a.rows_pad * kHeadDim;
+  float* inbox = pml + (size_t)a.rows_pad * 2;             // [n_splits][cap][kInboxStride]
+  const int kvh = blockIdx.x, split = blockIdx.y;
+  const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  attn_partial(a, kvh, split, dsm, tid, BAR_TEAM0, po, pml);
+  const int R = a.group * a.M;
+  const int n_items = R * 8;
+  const int cap = (n_items + a.n_splits - 1) / a.n_splits;   // items per merging CTA (upper bound)
+  // push: item -> (destination CTA, slot in its inbox), my partial goes to row `split` of that inbox
+  for (int item = tid; item < n_items; item += kAttnThreads) {
+    const int row = item >> 3, dseg = (item & 7) * 16;
+    const int dest = item % a.n_splits, li = item / a.n_splits;
+    float* dst = cluster.map_shared_rank(inbox, dest) + ((size_t)split * cap + li) * kInboxStride;
+    const float4* src = reinterpret_cast<const float4*>(po + (size_t)row * kHeadDim + dseg);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = src[i];
+    *reinterpret_cast<float2*>(dst + 16) = make_float2(pml[row * 2], pml[row * 2 + 1]);
+  }
+  cluster.sync();      // release / acquire: every push has landed
+  for (int li = tid; li < cap; li += kAttnThreads) {
+    const int item = li * a.n_splits + split;
+    if (item >= n_items) break;
+    const int row = item >> 3, dseg = (item & 7) * 16;
+    merge_splits_write(
+        a, kvh, row, dseg,
+        [&](int s) { return (const float*)(inbox + ((size_t)s * cap + li) * kInboxStride + 16); },
+        [&](int s) { return (const float*)(inbox + ((size_t)s * cap + li) * kInboxStride); });
+  }
+}
+
 __global__ void __launch_bounds__(kAttnThreads)
 attn_splitkv_kernel(const AttnArgs a) {
   __shared__ __align__(128) unsigned char sm_raw[kAttnTeamSmem];

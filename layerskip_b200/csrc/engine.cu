@@ -160,6 +160,7 @@ struct lsk_engine {
   // instead of launching kernels; programs live in device memory, one per graph key
   bool use_mega = false;               // opt-in (LSK_FLAG_MEGAKERNEL / LSK_MEGA=1): measured slower, see DESIGN.md
   bool attn_cluster = true;            // attention: cluster launch + DSMEM merge of the splits
+  bool attn_push = false;              // LSK_ATTN_PUSH=1: push-merge variant (one cluster barrier), unrun
   int mega_ring = 6;                   // ring stages of the megakernel (96 KiB)
   std::vector<StageDesc>* recording = nullptr;
   bool record_failed = false;
@@ -416,7 +417,9 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(e->kv_heads_l, e->n_splits);
       cfg.blockDim = dim3(kAttnThreads);
-      cfg.dynamicSmemBytes = kAttnTeamSmem + (size_t)a.rows_pad * (kHeadDim + 2) * 4;
+      cfg.dynamicSmemBytes = e->attn_push ? attn_push_smem_bytes(a.rows_pad)
+                                          : kAttnTeamSmem + (size_t)a.rows_pad * (kHeadDim + 2) * 4;
+      auto attn_kernel = e->attn_push ? attn_cluster_push_kernel : attn_cluster_kernel;
       cfg.stream = e->stream;
       cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -428,12 +431,12 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       e->launches += 1;
       e->capture_launches += 1;
       if (!e->profiling) {
-        CU(cudaLaunchKernelEx(&cfg, attn_cluster_kernel, a));
+        CU(cudaLaunchKernelEx(&cfg, attn_kernel, a));
       } else {
         cudaEvent_t ea, eb;
         cudaEventCreate(&ea); cudaEventCreate(&eb);
         cudaEventRecord(ea, e->stream);
-        cudaError_t err = cudaLaunchKernelEx(&cfg, attn_cluster_kernel, a);
+        cudaError_t err = cudaLaunchKernelEx(&cfg, attn_kernel, a);
         cudaEventRecord(eb, e->stream);
         e->prof_events.push_back({e->cur_class, {ea, eb}});
         CU(err);
@@ -846,6 +849,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->keep_logits = (c.flags & LSK_FLAG_KEEP_LOGITS) != 0;
   e->use_mega = ((c.flags & LSK_FLAG_MEGAKERNEL) || getenv("LSK_MEGA")) && !getenv("LSK_NO_MEGA");
   e->attn_cluster = !getenv("LSK_NO_ATTN_CLUSTER");
+  e->attn_push = e->attn_cluster && getenv("LSK_ATTN_PUSH") && atoi(getenv("LSK_ATTN_PUSH")) != 0;
   e->want_peer = c.tp_size > 1 && ((c.flags & LSK_FLAG_TP_ONESHOT) ||
                                    (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) != 0));
   if (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) == 2) e->peer_mode = 2;
@@ -941,6 +945,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   if (getenv("LSK_MEGA_TIMELINE")) TRY(alloc((void**)&e->timeline, (4097 + 4 * 4096 * 4) * 8));
   CU(cudaFuncSetAttribute(step_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   CU(cudaFuncSetAttribute(attn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CU(cudaFuncSetAttribute(attn_cluster_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   TRY(alloc((void**)&e->d_prompt, (size_t)e->max_pos * 4));
   TRY(alloc((void**)&e->state, sizeof(DevState)));
   TRY(alloc((void**)&e->gen_dev, sizeof(GenParams)));

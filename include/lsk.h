@@ -192,6 +192,12 @@ int lsk_plan_gemm(int64_t n_rows, int64_t k, int32_t m, int32_t pro, int32_t epi
 int lsk_test_pack(const void* w_bf16_dev, int64_t n, int64_t k, void* packed_out_dev);
 int lsk_test_gemm(const void* packed_dev, int64_t n, int64_t k, const void* x_bf16_dev,
                   int32_t m, float* y_dev, int32_t iters, float* avg_ms_out);
+/* tcgen05 LM head (csrc/lmhead_tc.cuh, opt-in): logits[m, n] = rmsnorm(x)[m, :] . W[n, :] with
+ * W natural bf16 [n, k], x fp32 [m, k], norm_w bf16 [k]; writes fp32 logits [m, n] and per row the
+ * arg-max (lowest index wins).  All pointers are device pointers. */
+int lsk_test_lmhead_tc(const void* w_bf16_dev, int64_t n, int64_t k, const float* x_f32_dev,
+                       const void* norm_w_bf16_dev, float eps, int32_t m, float* logits_dev,
+                       float* best_val_dev, int32_t* best_idx_dev, int32_t iters, float* avg_ms_out);
 
 #ifdef __cplusplus
 }

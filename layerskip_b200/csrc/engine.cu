@@ -23,6 +23,7 @@
 #include "gemm_skinny.cuh"
 #include "megakernel.cuh"
 #include "tp_peer.cuh"
+#include "lmhead_tc.cuh"
 #include "misc_kernels.cuh"
 #include "sampling.cuh"
 
@@ -96,6 +97,10 @@ struct lsk_engine {
   __nv_bfloat16* embed = nullptr;      // [vocab, hidden] natural (replicated)
   __nv_bfloat16* final_norm = nullptr;
   __nv_bfloat16* lm_head = nullptr;    // packed [vocab_l_pad, hidden]
+  // opt-in tcgen05 LM head (lmhead_tc.cuh): a second, canonical-layout copy of the head weights
+  bool lm_tc = false;
+  unsigned char* lm_head_tc = nullptr;   // [lm_tc_tiles][hidden / 64][16 KiB]
+  int lm_tc_tiles = 0, lm_tc_grid = 0, lm_tc_stages = 0;
   unsigned globals_loaded = 0;
 
   __nv_bfloat16* kpool = nullptr;      // [layer][page][kv_head][64][128]
@@ -578,7 +583,17 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
   a.part_val = e->cand_val; a.part_idx = e->cand_idx;
   a.next_W = after_W;
   a.next_bytes = after_W ? (after_bytes < e->l2_prefetch_bytes ? after_bytes : e->l2_prefetch_bytes) : 0;
-  if (!(e->ablate & (1u << CLS_LMHEAD))) TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
+  if (e->lm_tc && !e->recording) {
+    if (!(e->ablate & (1u << CLS_LMHEAD))) {
+      LmHeadTcArgs t{};
+      t.W = e->lm_head_tc; t.n_tiles = e->lm_tc_tiles; t.K = c.hidden; t.M = M; t.n_stages = e->lm_tc_stages;
+      t.x_f32 = a.x_f32; t.x_ld = a.x_ld; t.norm_w = a.norm_w; t.eps = a.eps;
+      t.logits = a.logits; t.logits_ld = a.logits_ld; t.n_valid_rows = a.n_valid_rows; t.vocab_off = a.vocab_off;
+      t.part_val = a.part_val; t.part_idx = a.part_idx;
+      CU(launch(e, lmhead_tc_kernel, dim3(e->lm_tc_grid), dim3(kTcThreads),
+                lmhead_tc_smem_bytes(c.hidden, e->lm_tc_stages), t));
+    }
+  } else if (!(e->ablate & (1u << CLS_LMHEAD))) TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
   e->cur_class = CLS_MISC;
   if (c.tp_size > 1 && e->gen.sample) {
     // every rank needs the whole distribution: all-gather the vocab shards of the M rows, lay them
@@ -894,6 +909,22 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->p_lm = make_plan(e->vocab_l_pad, c.hidden, e->sm_count);
   e->lm_cand = e->p_lm.n_tiles < e->sm_count ? e->p_lm.n_tiles : e->sm_count;
   if (const char* env = getenv("LSK_L2_PREFETCH_MB")) e->l2_prefetch_bytes = (size_t)atoi(env) << 20;
+  if (getenv("LSK_LMHEAD_TC") && atoi(getenv("LSK_LMHEAD_TC")) != 0) {
+    // tcgen05 LM head: needs hidden % 64 == 0 and the 16-token B operand + a >= 3-stage ring in
+    // shared memory (hidden <= 5120); otherwise stay on the mma.sync kernel, loudly
+    int st = kTcMaxStages;
+    while (st >= 3 && lmhead_tc_smem_bytes(c.hidden, st) > (size_t)kSmemMax) --st;
+    if (c.hidden % kTcStageK == 0 && st >= 3) {
+      e->lm_tc = true;
+      e->lm_tc_stages = st;
+      e->lm_tc_tiles = (e->vocab_l + kTcTileRows - 1) / kTcTileRows;
+      const int waves = (e->lm_tc_tiles + e->sm_count - 1) / e->sm_count;
+      e->lm_tc_grid = (e->lm_tc_tiles + waves - 1) / waves;        // even waves
+      e->lm_cand = e->lm_tc_grid;
+    } else {
+      fprintf(stderr, "[lsk] LSK_LMHEAD_TC ignored: hidden %d does not fit the tcgen05 LM head\n", c.hidden);
+    }
+  }
   e->max_rows = plan_sched(2, kMaxRows, PRO_RMS, EPI_QKV, e->p_qkv, e->sm_count).ok ? kMaxRows : 8;
 
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -919,6 +950,10 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   TRY(alloc((void**)&e->embed, (size_t)c.vocab * h * 2));
   TRY(alloc((void**)&e->final_norm, h * 2));
   TRY(alloc((void**)&e->lm_head, (size_t)e->vocab_l_pad * h * 2));
+  if (e->lm_tc) {
+    TRY(alloc((void**)&e->lm_head_tc, (size_t)e->lm_tc_tiles * kTcTileRows * h * 2));
+    CU(cudaFuncSetAttribute(lmhead_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  }
   e->pool_layer_elems = (size_t)e->n_pages * e->kv_heads_l * kPageTokens * kHeadDim;
   TRY(alloc((void**)&e->kpool, e->pool_layer_elems * c.n_layers * 2));
   TRY(alloc((void**)&e->vpool, e->pool_layer_elems * c.n_layers * 2));
@@ -990,7 +1025,7 @@ void lsk_destroy(lsk_engine* e) {
   for (auto& L : e->layers) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
   }
-  void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->kpool, e->vpool, e->page_table, e->rope,
+  void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->lm_head_tc, e->kpool, e->vpool, e->page_table, e->rope,
                   e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->logits_gath, e->logits_full, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
                   e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx, e->part_o,
                   e->part_ml, e->tickets, e->d_zero, e->d_prompt, e->state, e->gen_dev};
@@ -1116,6 +1151,11 @@ int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n) {
       case LSK_W_LM_HEAD:
         TRY(expect(c.vocab, h));
         TRY(pack(e, src, h, (int64_t)r * e->vocab_l, 0, e->vocab_l, h, e->lm_head, 0, MAP_PLAIN));
+        if (e->lm_tc) {
+          pack_canonical_kernel<<<148 * 8, 256, 0, e->stream>>>(src, h, (int64_t)r * e->vocab_l, e->vocab_l, h,
+                                                              reinterpret_cast<uint4*>(e->lm_head_tc), e->lm_tc_tiles);
+          CU(cudaGetLastError());
+        }
         e->globals_loaded |= 4u;
         break;
       case LSK_W_LN1:
@@ -1488,6 +1528,59 @@ int lsk_test_gemm(const void* packed, int64_t n, int64_t k, const void* x, int32
   CU(cudaEventDestroy(e1));
   CU(cudaStreamDestroy(tmp.stream));
   tmp.stream = nullptr;
+  return LSK_OK;
+}
+
+// tcgen05 LM head on caller-provided device buffers (unit test / micro-benchmark of lmhead_tc.cuh)
+int lsk_test_lmhead_tc(const void* w, int64_t n, int64_t k, const float* x, const void* norm_w, float eps,
+                       int32_t m, float* logits, float* best_val, int32_t* best_idx, int32_t iters,
+                       float* avg_ms) {
+  if (!w || !x || !norm_w || !best_val || !best_idx || n < 1 || k % kTcStageK || m < 1 || m > kMaxRows)
+    return fail(LSK_ERR_INVALID, "bad tcgen05 LM-head test shape");
+  int stages = kTcMaxStages;
+  while (stages >= 3 && lmhead_tc_smem_bytes((int)k, stages) > (size_t)kSmemMax) --stages;
+  if (stages < 3) return fail(LSK_ERR_INVALID, "hidden %lld does not fit the tcgen05 LM head", (long long)k);
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tiles = (int)((n + kTcTileRows - 1) / kTcTileRows);
+  const int waves = (n_tiles + sms - 1) / sms;
+  const int grid = (n_tiles + waves - 1) / waves;
+  unsigned char* canon = nullptr;
+  float* cval = nullptr;
+  int* cidx = nullptr;
+  CU(cudaMalloc((void**)&canon, (size_t)n_tiles * kTcTileRows * k * 2));
+  CU(cudaMalloc((void**)&cval, (size_t)grid * kMaxRows * 4));
+  CU(cudaMalloc((void**)&cidx, (size_t)grid * kMaxRows * 4));
+  pack_canonical_kernel<<<148 * 8, 256>>>((const __nv_bfloat16*)w, k, 0, n, k, reinterpret_cast<uint4*>(canon), n_tiles);
+  CU(cudaGetLastError());
+  CU(cudaFuncSetAttribute(lmhead_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  LmHeadTcArgs t{};
+  t.W = canon; t.n_tiles = n_tiles; t.K = (int)k; t.M = m; t.n_stages = stages;
+  t.x_f32 = x; t.x_ld = (int)k; t.norm_w = (const __nv_bfloat16*)norm_w; t.eps = eps;
+  t.logits = logits; t.logits_ld = (int)n; t.n_valid_rows = (int)n; t.vocab_off = 0;
+  t.part_val = cval; t.part_idx = cidx;
+  const size_t smem = lmhead_tc_smem_bytes((int)k, stages);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  lmhead_tc_kernel<<<grid, kTcThreads, smem>>>(t);
+  CU(cudaGetLastError());
+  rank_best_kernel<<<1, 256>>>(cval, cidx, grid, m, best_val, best_idx);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  if (iters > 0) {
+    CU(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) lmhead_tc_kernel<<<grid, kTcThreads, smem>>>(t);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = ms / iters;
+  }
+  CU(cudaEventDestroy(e0));
+  CU(cudaEventDestroy(e1));
+  cudaFree(canon); cudaFree(cval); cudaFree(cidx);
   return LSK_OK;
 }
 

@@ -7,8 +7,9 @@ set -x
 # 1. checkpoint-fed engine == state-dict-fed engine (1 GPU)
 timeout 300 python -m pytest tests/test_gpu_zz_checkpoint.py -x -q 2>&1 | tail -5 | tee gpurun_out/unrun_checkpoint.log
 # 1b. push-merge attention kernel == pull-merge kernel, and what it buys on the 7B round
-LSK_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_zz_experimental.py -x -q 2>&1 | tail -5 | tee gpurun_out/unrun_attn_push.log
+LSK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_experimental.py -q -s 2>&1 | tail -5 | tee gpurun_out/unrun_attn_push.log
 for v in 0 1; do LSK_ATTN_PUSH=$v timeout 300 python tools/profile_round.py llama2-7b 20 400 2>&1 | tail -2 | tee -a gpurun_out/unrun_attn_push.log; done
+LSK_LMHEAD_TC=1 timeout 300 python tools/profile_round.py llama2-7b 20 400 2>&1 | tail -2 | tee -a gpurun_out/unrun_attn_push.log
 # 2. one-shot peer collectives == NCCL path, bit for bit at TP=2; sampling under TP (2 GPUs)
 LSK_TEST_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_tp.py -x -q 2>&1 | tail -8 | tee gpurun_out/unrun_tp_oneshot.log
 # 3. what it buys: 13B at TP=2, NCCL vs one-shot (short runs)

@@ -5,6 +5,8 @@ arithmetic, the draft/verify/accept logic and the KV bookkeeping run in the CUDA
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
@@ -49,6 +51,15 @@ class Engine:
             tp_size=tp_size, attn_splits=attn_splits, flags=flags)
         self.max_ctx = max_ctx
         self.keep_logits = keep_logits
+        # refuse a configuration that cannot fit BEFORE cudaMalloc fails half-way (memory.py)
+        try:
+            free_bytes = torch.cuda.mem_get_info(self.device)[0]
+        except Exception:  # pragma: no cover - very old drivers
+            free_bytes = None
+        if free_bytes is not None:
+            from .memory import check_fits
+            check_fits(arch, free_bytes, max_ctx=max_ctx, tp_size=tp_size, keep_logits=keep_logits,
+                       sampling=False, lm_head_tc=os.environ.get("LSK_LMHEAD_TC", "0") not in ("", "0"))
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.lsk_create(C.byref(cfg), C.byref(handle)))

@@ -34,3 +34,25 @@ def test_baseline_configs_fit_a_b200_and_70b_needs_tp():
         check_fits(ARCHS["llama2-70b"], free, max_ctx=131072, tp_size=1)    # + 43 GB of KV does not
     with pytest.raises(MemoryError):
         check_fits(ARCHS["llama2-7b"], 8 * 10 ** 9, max_ctx=704)
+
+
+def test_engine_refuses_a_configuration_that_cannot_fit_before_touching_the_library(monkeypatch):
+    """Engine.__init__ runs the budget check first: with 8 GB 'free' a 7B engine must raise
+    MemoryError and lsk_create must never be called."""
+    import torch
+    from layerskip_b200 import _lib, engine
+
+    calls = []
+
+    class FakeLib:
+        def lsk_create(self, *a):
+            calls.append("create")
+            return -2
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (8 * 10 ** 9, 180 * 10 ** 9))
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib())
+    with pytest.raises(MemoryError, match="only 8.0 GB are free"):
+        engine.Engine(ARCHS["llama2-7b"], max_ctx=704)
+    assert calls == []

@@ -51,7 +51,11 @@ def parse_args():
     ap.add_argument("--max-steps", type=int, default=512)
     ap.add_argument("--alpha", type=float, default=1.0,
                     help="late-layer damping of the synthetic model (1.0 = pure random init)")
-    ap.add_argument("--tp", action="store_true", help="tensor-parallel over the N GPUs")
+    ap.add_argument("--tp", action="store_true", help="(default for N > 1) tensor-parallel over the N GPUs")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N > 1: make the independent-replicas leg the headline instead of tensor parallelism")
+    ap.add_argument("--deadline", type=float, default=800.0,
+                    help="seconds after which the watchdog prints the best line it has and exits")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the acceptance sweep / AR legs")
     ap.add_argument("--cpu-max-steps", type=int, default=0, help="reference arm: tokens per step")
@@ -289,6 +293,207 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+class Watchdog:
+    """A hung collective must not cost the driver its JSON line: at the deadline rank 0 prints the
+    best line it has (the headline if it finished, else an error line) and EVERY rank exits 0."""
+
+    def __init__(self, seconds: float, rank: int):
+        import threading
+        self.rank = rank
+        self.line = None
+        self.note = "started"
+        self._t = threading.Timer(seconds, self._fire)
+        self._t.daemon = True
+        self._t.start()
+
+    def _fire(self):
+        if self.rank == 0:
+            line = self.line or {"metric": METRIC, "value": None, "unit": UNIT,
+                                 "error": f"bench.py watchdog fired during: {self.note}"}
+            line.setdefault("extra", {})["watchdog"] = f"deadline hit during: {self.note}"
+            emit(json.dumps(line))
+        os._exit(0)
+
+    def cancel(self):
+        self._t.cancel()
+
+
+def measure_generations(strat, eng, model, prompts, gcfg, args, eos, first, count, e2e=False):
+    """`count` generations starting at prompt index `first`, device-timed: CUDA events on the
+    engine's stream around prefill and every round, inputs already resident."""
+    out = dict(tokens=0, dev_ms=0.0, bytes=0.0, accs=[], streams=[])
+    for i in range(count):
+        prompt = prompts[(first + i) % len(prompts)]
+        eng.begin(exit_layer=gcfg.exit_layer, max_steps=gcfg.max_steps, eos_token_ids=eos)
+        eng.prefill(prompt)
+        ms = eng.last_device_ms
+        toks, matches, drafted = [], 0, 0
+        while len(toks) < gcfg.max_steps:
+            d = min(gcfg.num_speculations, gcfg.max_steps - len(toks) - 1)
+            ctx = eng.kv_len
+            r = eng.round(d)
+            ms += eng.last_device_ms
+            out["bytes"] += eng.round_bytes(d, ctx)
+            toks += r.emitted
+            matches += r.n_matches
+            drafted += r.n_drafted
+            if eos[0] in toks:
+                toks = toks[: toks.index(eos[0])]
+                break
+        out["tokens"] += len(toks)
+        out["dev_ms"] += ms
+        out["accs"].append(matches / max(1, drafted))
+        out["streams"].append(toks)
+    return out
+
+
+def class_profile(eng, arch, tp, prompts, gcfg, eos, reps=5):
+    """Eager rounds with a CUDA-event pair around every launch -> per kernel class time / launches."""
+    eng.begin(exit_layer=gcfg.exit_layer, max_steps=gcfg.max_steps, eos_token_ids=eos)
+    eng.prefill(prompts[0])
+    for _ in range(2):
+        eng.round(gcfg.num_speculations)
+    cls_ms = {k: 0.0 for k in eng.KERNEL_CLASSES}
+    cls_n = {k: 0 for k in eng.KERNEL_CLASSES}
+    for _ in range(reps):
+        _r, ms, cnt, _tot = eng.profile_round(gcfg.num_speculations)
+        for k in ms:
+            cls_ms[k] += ms[k]
+            cls_n[k] += cnt[k]
+    a, t = arch, max(1, tp)
+    wb = {"qkv": 2.0 * (a.q_dim + 2 * a.kv_dim) * a.hidden / t, "o_proj": 2.0 * a.hidden * a.q_dim / t,
+          "gate_up": 2.0 * 2 * a.inter * a.hidden / t, "down": 2.0 * a.hidden * a.inter / t,
+          "lm_head": 2.0 * a.vocab * a.hidden / t}
+    return cls_ms, cls_n, wb, reps
+
+
+def ncu_traffic(arch_name, tp, cls):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r2_ncu_traffic.json, written by tools/ncu_traffic.py from the raw CSV export)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+            tab = json.load(f)
+        ent = tab.get(f"{arch_name}/tp{tp}", {}).get(cls)
+        return float(ent["dram_bytes_per_launch"]) if ent else None
+    except Exception:
+        return None
+
+
+def roofline_block(args, arch, tp, eng, prompts, gcfg, eos, meas, peak, peak_kind):
+    cls_ms, cls_n, wb, reps = class_profile(eng, arch, tp, prompts, gcfg, eos)
+    gemm_bytes = sum(wb[k] * cls_n[k] for k in wb)
+    gemm_ms = sum(cls_ms[k] for k in wb)
+    gemm_launches = sum(cls_n[k] for k in wb)
+    # dominant kernel = the instantiation with the largest share of device time (gate/up projection)
+    dom = max(wb, key=lambda k: cls_ms[k])
+    dom_us = cls_ms[dom] * 1e3 / max(1, cls_n[dom])
+    achieved = wb[dom] / (dom_us * 1e-6) / 1e9
+    whole = meas["bytes"] / (meas["dev_ms"] * 1e-3) / 1e9
+    return {"bound": "hbm",
+            "kernel": f"lsk::gemm_skinny_kernel<1,PRO_RMS/BF16,EPI_*> [{dom}] — TMA-ring weight-streaming GEMM",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+            "bytes_per_launch": wb[dom], "avg_launch_us": dom_us,
+            "traffic": ncu_traffic(args.arch, tp, dom),
+            "how": "algorithmic bytes (packed weight bytes of the GEMM) / mean CUDA-event duration of "
+                   "its launches in eager rounds on the engine stream (includes launch gaps that graph "
+                   "replay + PDL hide); traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                   "from the ncu capture under profiles/ (null when no capture of this config is committed)",
+            "all_gemm_launches": {"achieved": gemm_bytes / (gemm_ms * 1e-3) / 1e9,
+                                  "frac": gemm_bytes / (gemm_ms * 1e-3) / 1e9 / peak,
+                                  "launches_per_round": gemm_launches / reps},
+            "per_class": {k: {"launches_per_round": cls_n[k] / reps, "ms_per_round": cls_ms[k] / reps,
+                              "gbs": (wb[k] * cls_n[k] / (cls_ms[k] * 1e-3) / 1e9) if k in wb and cls_ms[k] > 0 else None}
+                          for k in eng.KERNEL_CLASSES},
+            "whole_path": {"achieved": whole, "frac": whole / peak,
+                           "note": "algorithmic bytes of every round per GPU (weights + KV, SURVEY.md 8(d)) / "
+                                   "device time of the timed region (graph replay)"}}
+
+
+def tp_leg(arch_name, exit_layer, args, rank, world, peak, steps=2, warmup=1, single_gpu_check=True):
+    """One tensor-parallel measurement over all `world` GPUs: ONE model sharded by heads / FFN
+    columns / vocab, one-shot all-reduces over peer-mapped HBM after O-proj and down-proj.  Returns
+    tokens/s (device-timed, max over ranks), the per-GPU roofline fraction, and three correctness
+    bits: every rank holds the same token stream, speculative == autoregressive on the sharded
+    engine, and the stream's agreement with a single-GPU engine of the same model (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from layerskip_b200 import GenerationConfig
+    from layerskip_b200.strategy import (B200AutoRegressiveGenerationStrategy,
+                                         B200SelfSpeculativeGenerationStrategy)
+    from layerskip_b200.synthetic import synthetic_prompts
+    from layerskip_b200.weights import ARCHS, SyntheticLlama
+    arch = ARCHS[arch_name]
+    if arch.heads % world or arch.kv_heads % world:
+        return {"skipped": f"{arch.kv_heads} kv heads do not divide by {world} ranks"}
+    model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=exit_layer, device="cuda")
+    max_ctx = ((args.prompt_len + args.max_steps + 64 + 63) // 64) * 64
+    prompts = synthetic_prompts(arch.vocab, 8, args.prompt_len)
+    eos = [arch.vocab - 1]
+    gcfg = GenerationConfig(max_steps=args.max_steps, exit_layer=exit_layer,
+                            num_speculations=args.num_speculations, sample=False,
+                            generation_strategy="self_speculative")
+    short = GenerationConfig(max_steps=48, exit_layer=exit_layer, num_speculations=args.num_speculations,
+                             sample=False, generation_strategy="self_speculative")
+    single = None
+    if single_gpu_check and rank == 0:
+        s1 = B200SelfSpeculativeGenerationStrategy(max_ctx=max_ctx)
+        single = s1.generate_token_ids(model, prompts[0], eos, short).predicted_tokens
+        s1.engines.close()
+    dist.barrier()
+    strat = B200SelfSpeculativeGenerationStrategy(max_ctx=max_ctx, tp_rank=rank, tp_size=world)
+    eng = strat.engine_for(model)
+    ar = B200AutoRegressiveGenerationStrategy(engine_cache=strat.engines)
+    spec_tokens = strat.generate_token_ids(model, prompts[0], eos, short).predicted_tokens
+    ar_tokens = ar.generate_token_ids(model, prompts[0], eos,
+                                      GenerationConfig(max_steps=48, exit_layer=-1, num_speculations=-1,
+                                                       sample=False)).predicted_tokens
+    for i in range(warmup):
+        measure_generations(strat, eng, model, prompts, gcfg, args, eos, i, 1, e2e=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    m = measure_generations(strat, eng, model, prompts, gcfg, args, eos, warmup, steps, e2e=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([m["dev_ms"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t.item()) * 1e-3
+    # every rank must hold the same stream: compare a hash of all timed tokens
+    h = 1469598103934665603
+    for tok in [x for st in m["streams"] for x in st] + spec_tokens:
+        h = ((h ^ (tok + 1)) * 1099511628211) & 0x7FFFFFFFFFFFFFFF
+    hv = torch.tensor([h], dtype=torch.int64, device="cuda")
+    lo, hi = hv.clone(), hv.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    cls_ms, cls_n, wb, reps = class_profile(eng, arch, world, prompts, gcfg, eos, reps=3)
+    whole = m["bytes"] / (m["dev_ms"] * 1e-3) / 1e9
+    res = {"arch": arch_name, "tp": world, "exit_layer": exit_layer,
+           "tokens_per_s": m["tokens"] / dev_s, "ms_per_generation": dev_s * 1e3 / steps,
+           "generations": steps, "acceptance_rate": sum(m["accs"]) / max(1, len(m["accs"])),
+           "per_gpu_hbm_gbs": whole, "per_gpu_roofline_frac": whole / peak,
+           "collectives": {"0": "nccl", "2": "peer one-shot LL, push fused into the GEMM epilogue",
+                           "3": "peer one-shot, fence + flag"}.get(os.environ.get("LSK_TP_ONESHOT", "1"),
+                                                                    "peer one-shot LL (flag in data)"),
+           "per_class": {k: {"launches_per_round": cls_n[k] / reps, "ms_per_round": cls_ms[k] / reps}
+                         for k in eng.KERNEL_CLASSES},
+           "ranks_agree": bool(int(lo.item()) == int(hi.item())),
+           "spec_equals_ar_on_tp_engine": spec_tokens == ar_tokens}
+    if single is not None:
+        n_same = 0
+        for x, y in zip(single, spec_tokens):
+            if x != y:
+                break
+            n_same += 1
+        res["single_gpu_prefix_match"] = f"{n_same}/{len(single)}"
+        res["tokens_match_single_gpu"] = n_same == len(single)
+    strat.engines.close()
+    del model
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -302,89 +507,30 @@ def run_b200_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
+    dog = Watchdog(args.deadline, rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    tp = world if (args.tp and world > 1) else 1
+    # N > 1: the headline is ONE model tensor-parallel over the N GPUs (strong scaling, the split
+    # north_star names); independent replicas (weak scaling) are reported in extra.replicas
+    tp = world if (world > 1 and not args.replicas) else 1
 
     arch = ARCHS[args.arch]
+    if tp > 1 and (arch.heads % tp or arch.kv_heads % tp):
+        raise SystemExit(f"{args.arch}: {arch.kv_heads} kv heads do not divide by {tp} ranks")
     model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=args.exit_layer, device="cuda")
     max_ctx = ((args.prompt_len + args.max_steps + 64 + 63) // 64) * 64
-    strat = B200SelfSpeculativeGenerationStrategy(
-        max_ctx=max_ctx, tp_rank=rank if tp > 1 else 0, tp_size=tp)
-    eng = strat.engine_for(model)
-    prompts = synthetic_prompts(arch.vocab, 8 * max(1, world), args.prompt_len)
-    if tp == 1:
-        prompts = prompts[rank::world]       # replicas: disjoint prompt streams per GPU
+    eos = [arch.vocab - 1]
     gcfg = GenerationConfig(max_steps=args.max_steps, exit_layer=args.exit_layer,
                             num_speculations=args.num_speculations, sample=False,
                             generation_strategy="self_speculative")
-    eos = [arch.vocab - 1]
-
-    def one_generation(i):
-        """Returns (tokens, device_ms, wall_s, acceptance, bytes)."""
-        prompt = prompts[i % len(prompts)]
-        dev_ms = 0.0
-        alg_bytes = 0.0
-        # device-timed leg: identical calls, timed with the engine's CUDA events
-        eng.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
-        eng.prefill(prompt)
-        dev_ms += eng.last_device_ms
-        out, matches, drafted = [], 0, 0
-        while len(out) < args.max_steps:
-            d = min(args.num_speculations, args.max_steps - len(out) - 1)
-            ctx = eng.kv_len
-            r = eng.round(d)
-            dev_ms += eng.last_device_ms
-            alg_bytes += eng.round_bytes(d, ctx)
-            out += r.emitted
-            matches += r.n_matches
-            drafted += r.n_drafted
-            if eos[0] in out:
-                out = out[: out.index(eos[0])]
-                break
-        return len(out), dev_ms, matches / max(1, drafted), alg_bytes, len(out)
-
-    def one_generation_e2e(i):
-        prompt = prompts[i % len(prompts)]
-        t0 = time.perf_counter()
-        res = strat.generate_token_ids(model, prompt, eos, gcfg)
-        return len(res.predicted_tokens), time.perf_counter() - t0, len(strat.last_rounds)
+    prompts = synthetic_prompts(arch.vocab, 8 * max(1, world), args.prompt_len)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        one_generation(i)
-    barrier()
-    launches0 = eng.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    tok_dev = 0
-    dev_ms_total = 0.0
-    bytes_total = 0.0
-    accs = []
-    for i in range(args.steps):
-        n, ms, acc, b, _ = one_generation(args.warmup + i)
-        tok_dev += n
-        dev_ms_total += ms
-        bytes_total += b
-        accs.append(acc)
-    barrier()
-    launches = eng.launch_count - launches0
-    # e2e leg through the plug-in call (wall clock, host buffers)
-    tok_e2e, wall_total, rounds_total = 0, 0.0, 0
-    for i in range(args.steps):
-        n, s, nr = one_generation_e2e(args.warmup + i)
-        tok_e2e += n
-        wall_total += s
-        rounds_total += nr
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
 
     def allsum(x):
         if world == 1:
@@ -400,189 +546,302 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    t_dev = allmax(dev_ms_total) * 1e-3
-    t_wall = allmax(wall_total)
+    # ---- correctness reference for the TP headline: the single-GPU engine's tokens (rank 0)
+    single_tokens = None
+    short = GenerationConfig(max_steps=48, exit_layer=args.exit_layer, num_speculations=args.num_speculations,
+                             sample=False, generation_strategy="self_speculative")
+    if tp > 1:
+        dog.note = "single-GPU reference tokens"
+        if rank == 0:
+            s1 = B200SelfSpeculativeGenerationStrategy(max_ctx=max_ctx)
+            single_tokens = s1.generate_token_ids(model, prompts[0], eos, short).predicted_tokens
+            s1.engines.close()
+        barrier()
+
+    dog.note = "engine creation / weight upload"
+    strat = B200SelfSpeculativeGenerationStrategy(
+        max_ctx=max_ctx, tp_rank=rank if tp > 1 else 0, tp_size=tp)
+    eng = strat.engine_for(model)
+    my_prompts = prompts if tp > 1 else prompts[rank::world]   # replicas: disjoint prompt streams per GPU
+
+    dog.note = "warm-up"
+    for i in range(args.warmup):
+        measure_generations(strat, eng, model, my_prompts, gcfg, args, eos, i, 1, e2e=False)
+    barrier()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dog.note = "timed region"
+    meas = measure_generations(strat, eng, model, my_prompts, gcfg, args, eos, args.warmup, args.steps, e2e=False)
+    barrier()
+    launches = eng.launch_count - launches0
+    # e2e leg through the plug-in call (wall clock, host ids in / host ids out, every copy and the
+    # per-round sync inside the region)
+    e2e = dict(tokens_e2e=0, wall=0.0, rounds=0)
+    for i in range(args.steps):
+        prompt = my_prompts[(args.warmup + i) % len(my_prompts)]
+        w0 = time.perf_counter()
+        res = strat.generate_token_ids(model, prompt, eos, gcfg)
+        e2e["wall"] += time.perf_counter() - w0
+        e2e["tokens_e2e"] += len(res.predicted_tokens)
+        e2e["rounds"] += len(strat.last_rounds)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t_dev = allmax(meas["dev_ms"]) * 1e-3
+    t_wall = allmax(e2e["wall"])
     if tp > 1:        # every rank holds the same stream of tokens
-        tokens_total, tokens_total_e2e = tok_dev, tok_e2e
+        tokens_total, tokens_total_e2e = meas["tokens"], e2e["tokens_e2e"]
     else:
-        tokens_total, tokens_total_e2e = allsum(tok_dev), allsum(tok_e2e)
+        tokens_total, tokens_total_e2e = allsum(meas["tokens"]), allsum(e2e["tokens_e2e"])
     value = tokens_total / t_dev
     e2e_value = tokens_total_e2e / t_wall
+    peak, peak_kind = measured_peaks()
+
+    tp_check = None
+    if tp > 1:
+        dog.note = "TP correctness bits"
+        from layerskip_b200.strategy import B200AutoRegressiveGenerationStrategy
+        spec_tokens = strat.generate_token_ids(model, prompts[0], eos, short).predicted_tokens
+        ar_tokens = B200AutoRegressiveGenerationStrategy(engine_cache=strat.engines).generate_token_ids(
+            model, prompts[0], eos, GenerationConfig(max_steps=48, exit_layer=-1, num_speculations=-1,
+                                                     sample=False)).predicted_tokens
+        h = 1469598103934665603
+        for tok in [x for st in meas["streams"] for x in st] + spec_tokens:
+            h = ((h ^ (tok + 1)) * 1099511628211) & 0x7FFFFFFFFFFFFFFF
+        hv = torch.tensor([h], dtype=torch.int64, device="cuda")
+        lo, hi = hv.clone(), hv.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        tp_check = {"ranks_agree": bool(int(lo.item()) == int(hi.item())),
+                    "spec_equals_ar_on_tp_engine": spec_tokens == ar_tokens}
+        if single_tokens is not None:
+            n_same = 0
+            for x, y in zip(single_tokens, spec_tokens):
+                if x != y:
+                    break
+                n_same += 1
+            tp_check["single_gpu_prefix_match"] = f"{n_same}/{len(single_tokens)}"
+            tp_check["tokens_match_single_gpu"] = n_same == len(single_tokens)
 
     # ---- roofline of the dominant kernel (weight-streaming skinny GEMM), measured live
-    peak, peak_kind = measured_peaks()
+    dog.note = "per-class profile"
     roof = None
-    extra = {}
     if rank == 0 or tp > 1:       # tensor-parallel: every rank must issue the same engine calls
-        eng.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
-        eng.prefill(prompts[0])
-        for _ in range(2):
-            eng.round(args.num_speculations)
-        cls_ms = {k: 0.0 for k in eng.KERNEL_CLASSES}
-        cls_n = {k: 0 for k in eng.KERNEL_CLASSES}
-        reps = 5
-        for _ in range(reps):
-            _r, ms, cnt, _tot = eng.profile_round(args.num_speculations)
-            for k in ms:
-                cls_ms[k] += ms[k]
-                cls_n[k] += cnt[k]
-        a = arch
-        t = max(1, tp)
-        wb = {"qkv": 2.0 * (a.q_dim + 2 * a.kv_dim) * a.hidden / t, "o_proj": 2.0 * a.hidden * a.q_dim / t,
-              "gate_up": 2.0 * 2 * a.inter * a.hidden / t, "down": 2.0 * a.hidden * a.inter / t,
-              "lm_head": 2.0 * a.vocab * a.hidden / t}
-        gemm_bytes = sum(wb[k] * cls_n[k] for k in wb)
-        gemm_ms = sum(cls_ms[k] for k in wb)
-        gemm_launches = sum(cls_n[k] for k in wb)
-        # dominant kernel = the single instantiation with the largest share of device time:
-        # gemm_skinny_kernel<1, PRO_RMS, EPI_SILU> (gate/up projection, ~30 % of a round)
-        dom = max(wb, key=lambda k: cls_ms[k])
-        dom_us = cls_ms[dom] * 1e3 / max(1, cls_n[dom])
-        achieved = wb[dom] / (dom_us * 1e-6) / 1e9
-        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-        # (profiles/r1_final_kernels.md): 199.7 MB read + 3.5 MB written for 180.4 MB algorithmic
-        traffic = 203.2e6 if (args.arch == "llama2-7b" and tp == 1 and dom == "gate_up") else None
-        roof = {"bound": "hbm",
-                "kernel": f"lsk::gemm_skinny_kernel<1,PRO_RMS/BF16,EPI_*> [{dom}] — TMA-ring weight-streaming GEMM",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                "bytes_per_launch": wb[dom], "avg_launch_us": dom_us, "traffic": traffic,
-                "how": "algorithmic bytes (packed weight bytes of the GEMM) / mean CUDA-event duration of "
-                       "its launches in eager rounds on the engine stream (includes launch gaps that graph "
-                       "replay + PDL hide); traffic from the ncu capture under profiles/",
-                "all_gemm_launches": {"achieved": gemm_bytes / (gemm_ms * 1e-3) / 1e9,
-                                      "frac": gemm_bytes / (gemm_ms * 1e-3) / 1e9 / peak,
-                                      "launches_per_round": gemm_launches / reps},
-                "per_class": {k: {"launches_per_round": cls_n[k] / reps,
-                                  "ms_per_round": cls_ms[k] / reps,
-                                  "gbs": (wb[k] * cls_n[k] / (cls_ms[k] * 1e-3) / 1e9) if k in wb and cls_ms[k] > 0 else None}
-                              for k in eng.KERNEL_CLASSES},
-                "whole_path": {"achieved": bytes_total / (dev_ms_total * 1e-3) / 1e9,
-                               "frac": bytes_total / (dev_ms_total * 1e-3) / 1e9 / peak,
-                               "note": "algorithmic bytes of every round (weights + KV, SURVEY.md 8(d)) / device time of the timed region (graph replay)"}}
+        roof = roofline_block(args, arch, tp, eng, my_prompts, gcfg, eos, meas, peak, peak_kind)
 
-    cpu_baseline = None
+    acc_mean = sum(meas["accs"]) / max(1, len(meas["accs"]))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_dev * 1e3 / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "acceptance_rate": acc_mean,
+        "config": {"workload": f"{args.arch} arch, random-init (alpha={args.alpha}), "
+                               f"exit_layer={args.exit_layer}, num_speculations={args.num_speculations}, "
+                               f"greedy, {args.prompt_len}-id synthetic prompts, {args.max_steps}-token continuations",
+                   "parallelism": f"tp{tp}" if tp > 1 else f"replicas{world}",
+                   **({"tp_collectives": {"0": "nccl", "2": "peer one-shot LL, push fused into the GEMM epilogue",
+                                          "3": "peer one-shot, fence + flag"}.get(
+                                              os.environ.get("LSK_TP_ONESHOT", "1"),
+                                              "peer one-shot LL kernel (flag in data, csrc/tp_peer.cuh)")}
+                      if tp > 1 else {}),
+                   "l2": "inputs_exceed_l2 (weights 13.5 GB >> 126 MB L2)",
+                   "step": "one full generation (prefill + rounds)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * args.prompt_len,
+                "d2h_bytes_per_step": int(e2e["rounds"] / max(1, args.steps)) * 212},
+        "gpu_launches": int(launches),
+        "roofline": roof, "cpu_baseline": None, "extra": {},
+    }
+    if tp_check is not None:
+        line["tp_check"] = tp_check
+    dog.line = line
+    extra = line["extra"]
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dog.note = "cpu baseline"
         try:
             sd = model.state_dict(dtype=torch.bfloat16, device="cpu")
             w, w_dtype = cpu_weights(sd, arch)
             del sd
             cores = cpu_threads()
             t0 = time.perf_counter()
-            with time_limit(100):
-                n_cpu, _probe = cpu_sized_sample(args, w, arch, prompts, 20.0)
+            with time_limit(150):
+                n_cpu, _probe = cpu_sized_sample(args, w, arch, prompts, 30.0)
                 toks, secs, _acc = cpu_reference_run(args, w, arch, prompts, 1, n_cpu)
-            cpu_baseline = {"value": toks / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                            "cpu": cpu_model_name(),
-                            "sample": f"1 generation x {n_cpu} tokens, prompt {args.prompt_len} ids "
-                                      f"(prefill included), oracle port in torch {w_dtype} on {cores} threads; "
-                                      f"{time.perf_counter() - t0:.1f} s of CPU work incl. sizing probe"}
+            line["cpu_baseline"] = {"value": toks / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "cpu": cpu_model_name(),
+                                    "sample": f"1 generation x {n_cpu} tokens, prompt {args.prompt_len} ids "
+                                              f"(prefill included), oracle port in torch {w_dtype} on {cores} threads; "
+                                              f"{time.perf_counter() - t0:.1f} s of CPU work incl. sizing probe"}
             del w
         except Exception as exc:  # pragma: no cover
-            cpu_baseline = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                            "sample": f"failed: {exc!r}"}
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                                    "sample": f"failed: {exc!r}"}
 
     if rank == 0 and not args.no_extra and world == 1:
-        # informative legs: autoregressive on the same engine
+        dog.note = "extra legs"
+        single_gpu_extras(args, arch, strat, eng, model, prompts, eos, extra)
+
+    strat.engines.close()
+    del model
+    torch.cuda.empty_cache()
+
+    if world > 1 and not args.no_extra:
+        # ---- the other parallel legs of BASELINE.json's configs on the same N GPUs
+        legs = {}
         try:
-            eng.begin(exit_layer=-1, max_steps=args.max_steps, eos_token_ids=eos)
-            eng.prefill(prompts[0])
-            ms, nb = eng.last_device_ms, 0.0
-            for _ in range(128):
-                ctx = eng.kv_len
-                eng.ar_step()
-                ms += eng.last_device_ms
-                nb += eng.ar_bytes(ctx)
-            extra["autoregressive_same_engine"] = {"tokens_per_s": 128 / (ms * 1e-3),
-                                                   "hbm_gbs": nb / (ms * 1e-3) / 1e9}
+            if tp > 1:
+                dog.note = "replicas leg"
+                legs_rep = replicas_leg(args, rank, world, local_rank)
+                if rank == 0:
+                    extra["replicas"] = legs_rep
+            dog.note = "13B tensor-parallel leg"
+            legs["llama2-13b"] = tp_leg("llama2-13b", 8, args, rank, world, peak)
+            if world == 8:
+                dog.note = "70B tensor-parallel leg"
+                legs["llama2-70b"] = tp_leg("llama2-70b", 10, args, rank, world, peak, single_gpu_check=False)
         except Exception as exc:  # pragma: no cover
-            extra["autoregressive_same_engine"] = {"error": repr(exc)}
-        # acceptance-controlled legs: o_proj/down_proj of layers >= E damped by
-        # alpha; same architecture, prompts and settings, one 512-token generation each
-        sweep = []
-        for alpha in ([] if args.alpha != 1.0 else [0.3, 0.1, 0.03]):
-            try:
-                strat.engines.close()
-                m2 = SyntheticLlama(arch, seed=0, alpha=alpha, damp_from=args.exit_layer, device="cuda")
-                e2 = strat.engine_for(m2)
-                tot_ms, n_tok, mt, dr = 0.0, 0, 0, 0
-                for rep in range(2):        # rep 0 warms the graphs up
-                    e2.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
-                    e2.prefill(prompts[1])
-                    ms = e2.last_device_ms
-                    out = []
-                    while len(out) < args.max_steps:
-                        r = e2.round(min(args.num_speculations, args.max_steps - len(out) - 1))
-                        ms += e2.last_device_ms
-                        out += r.emitted
-                        if rep == 1:
-                            mt += r.n_matches
-                            dr += r.n_drafted
-                    if rep == 1:
-                        tot_ms, n_tok = ms, len(out)
-                sweep.append({"alpha": alpha, "acceptance_rate": mt / max(1, dr),
-                              "tokens_per_s": n_tok / (tot_ms * 1e-3)})
-                del m2
-            except Exception as exc:  # pragma: no cover
-                sweep.append({"alpha": alpha, "error": repr(exc)})
-        if sweep:
-            extra["acceptance_sweep"] = sweep
-        # the reference's DEFAULT decoding mode (sample=True, T=0.6, top_p=0.9; generator_base.py:39-42)
+            legs["error"] = repr(exc)
+        if rank == 0:
+            extra["tp"] = legs
+
+    if rank == 0:
+        dog.cancel()
+        emit(json.dumps(line))
+    else:
+        dog.cancel()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def replicas_leg(args, rank, world, local_rank):
+    """N independent single-GPU engines serving disjoint prompt streams (weak scaling, no
+    data-path collective): aggregate tokens/s = all tokens / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    from layerskip_b200 import GenerationConfig
+    from layerskip_b200.strategy import B200SelfSpeculativeGenerationStrategy
+    from layerskip_b200.synthetic import synthetic_prompts
+    from layerskip_b200.weights import ARCHS, SyntheticLlama
+    arch = ARCHS[args.arch]
+    model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=args.exit_layer, device="cuda")
+    max_ctx = ((args.prompt_len + args.max_steps + 64 + 63) // 64) * 64
+    strat = B200SelfSpeculativeGenerationStrategy(max_ctx=max_ctx)
+    eng = strat.engine_for(model)
+    prompts = synthetic_prompts(arch.vocab, 8 * world, args.prompt_len)[rank::world]
+    eos = [arch.vocab - 1]
+    gcfg = GenerationConfig(max_steps=args.max_steps, exit_layer=args.exit_layer,
+                            num_speculations=args.num_speculations, sample=False,
+                            generation_strategy="self_speculative")
+    measure_generations(strat, eng, model, prompts, gcfg, args, eos, 0, 1, e2e=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    m = measure_generations(strat, eng, model, prompts, gcfg, args, eos, 1, 2, e2e=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([m["dev_ms"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = torch.tensor([float(m["tokens"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(n)
+    strat.engines.close()
+    del model
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return {"parallelism": f"replicas{world}", "scaling": "weak", "generations_per_rank": 2,
+            "tokens_per_s": float(n.item()) / (float(t.item()) * 1e-3),
+            "note": "independent 7B engines, disjoint prompt streams, no data-path collective"}
+
+
+def single_gpu_extras(args, arch, strat, eng, model, prompts, eos, extra):
+    """Informative single-GPU legs: autoregressive on the same engine, acceptance-controlled
+    models, the reference's default sampling mode."""
+    import torch
+    from layerskip_b200.weights import SyntheticLlama
+    try:
+        eng.begin(exit_layer=-1, max_steps=args.max_steps, eos_token_ids=eos)
+        eng.prefill(prompts[0])
+        ms, nb = eng.last_device_ms, 0.0
+        for _ in range(128):
+            ctx = eng.kv_len
+            eng.ar_step()
+            ms += eng.last_device_ms
+            nb += eng.ar_bytes(ctx)
+        extra["autoregressive_same_engine"] = {"tokens_per_s": 128 / (ms * 1e-3),
+                                               "hbm_gbs": nb / (ms * 1e-3) / 1e9}
+    except Exception as exc:  # pragma: no cover
+        extra["autoregressive_same_engine"] = {"error": repr(exc)}
+    # prefill alone (tcgen05 GEMM path): device time of lsk_prefill for 128 and 1024 prompt ids
+    try:
+        pf = {}
+        for n in (128, 1024):
+            if n + 8 > eng.max_ctx:
+                continue
+            ids = (prompts[0] * (n // len(prompts[0]) + 1))[:n]
+            eng.begin(exit_layer=args.exit_layer, max_steps=4, eos_token_ids=eos)
+            eng.prefill(ids)
+            eng.begin(exit_layer=args.exit_layer, max_steps=4, eos_token_ids=eos)
+            eng.prefill(ids)
+            pf[str(n)] = {"ms": eng.last_device_ms}
+        extra["prefill_ms"] = pf
+    except Exception as exc:  # pragma: no cover
+        extra["prefill_ms"] = {"error": repr(exc)}
+    # acceptance-controlled legs (SURVEY.md App. C): o_proj/down_proj of layers >= E damped by
+    # alpha; same architecture, prompts and settings, one 512-token generation each
+    sweep = []
+    for alpha in ([] if args.alpha != 1.0 else [0.3, 0.1, 0.03]):
         try:
-            eng_s = strat.engine_for(model) if args.alpha == 1.0 and not sweep else None
-            if eng_s is None:
-                strat.engines.close()
-                eng_s = strat.engine_for(model)
+            strat.engines.close()
+            m2 = SyntheticLlama(arch, seed=0, alpha=alpha, damp_from=args.exit_layer, device="cuda")
+            e2 = strat.engine_for(m2)
             tot_ms, n_tok, mt, dr = 0.0, 0, 0, 0
-            for rep in range(2):
-                eng_s.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos,
-                            sample=True, temperature=0.6, top_k=0, top_p=0.9, seed=1234 + rep)
-                eng_s.prefill(prompts[2 % len(prompts)])
-                ms = eng_s.last_device_ms
+            for rep in range(2):        # rep 0 warms the graphs up
+                e2.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos)
+                e2.prefill(prompts[1])
+                ms = e2.last_device_ms
                 out = []
                 while len(out) < args.max_steps:
-                    r = eng_s.round(min(args.num_speculations, args.max_steps - len(out) - 1))
-                    ms += eng_s.last_device_ms
+                    r = e2.round(min(args.num_speculations, args.max_steps - len(out) - 1))
+                    ms += e2.last_device_ms
                     out += r.emitted
                     if rep == 1:
                         mt += r.n_matches
                         dr += r.n_drafted
                 if rep == 1:
                     tot_ms, n_tok = ms, len(out)
-            extra["sampling_T0.6_top_p0.9"] = {"acceptance_rate": mt / max(1, dr),
-                                               "tokens_per_s": n_tok / (tot_ms * 1e-3)}
+            sweep.append({"alpha": alpha, "acceptance_rate": mt / max(1, dr),
+                          "tokens_per_s": n_tok / (tot_ms * 1e-3)})
+            del m2
         except Exception as exc:  # pragma: no cover
-            extra["sampling_T0.6_top_p0.9"] = {"error": repr(exc)}
-
-    if rank == 0:
-        acc_mean = sum(accs) / max(1, len(accs))
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_dev * 1e3 / max(1, args.steps),
-            "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "acceptance_rate": acc_mean,
-            "config": {"workload": f"{args.arch} arch, random-init (alpha={args.alpha}), "
-                                   f"exit_layer={args.exit_layer}, num_speculations={args.num_speculations}, "
-                                   f"greedy, {args.prompt_len}-id synthetic prompts, {args.max_steps}-token continuations",
-                       "parallelism": f"tp{tp}" if tp > 1 else f"replicas{world}",
-                       **({"tp_collectives": {"": "nccl", "0": "nccl", "2": "peer-oneshot, push fused into "
-                                              "the GEMM epilogue (csrc/tp_peer.cuh)"}.get(
-                                                  os.environ.get("LSK_TP_ONESHOT", "0"),
-                                                  "peer-oneshot (csrc/tp_peer.cuh)")}
-                          if tp > 1 else {}),
-                       "l2": "inputs_exceed_l2 (weights 13.5 GB >> 126 MB L2)",
-                       "step": "one full generation (prefill + rounds)"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * args.prompt_len,
-                    "d2h_bytes_per_step": int(rounds_total / max(1, args.steps)) * 212},
-            "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu_baseline, "extra": extra,
-        }
-        emit(json.dumps(line))
-    strat.engines.close()
-    if world > 1:
-        dist.destroy_process_group()
+            sweep.append({"alpha": alpha, "error": repr(exc)})
+    if sweep:
+        extra["acceptance_sweep"] = sweep
+    # the reference's DEFAULT decoding mode (sample=True, T=0.6, top_p=0.9; generator_base.py:39-42)
+    try:
+        strat.engines.close()
+        eng_s = strat.engine_for(model)
+        tot_ms, n_tok, mt, dr = 0.0, 0, 0, 0
+        for rep in range(2):
+            eng_s.begin(exit_layer=args.exit_layer, max_steps=args.max_steps, eos_token_ids=eos,
+                        sample=True, temperature=0.6, top_k=0, top_p=0.9, seed=1234 + rep)
+            eng_s.prefill(prompts[2 % len(prompts)])
+            ms = eng_s.last_device_ms
+            out = []
+            while len(out) < args.max_steps:
+                r = eng_s.round(min(args.num_speculations, args.max_steps - len(out) - 1))
+                ms += eng_s.last_device_ms
+                out += r.emitted
+                if rep == 1:
+                    mt += r.n_matches
+                    dr += r.n_drafted
+            if rep == 1:
+                tot_ms, n_tok = ms, len(out)
+        extra["sampling_T0.6_top_p0.9"] = {"acceptance_rate": mt / max(1, dr),
+                                           "tokens_per_s": n_tok / (tot_ms * 1e-3)}
+    except Exception as exc:  # pragma: no cover
+        extra["sampling_T0.6_top_p0.9"] = {"error": repr(exc)}
 
 
 _REAL_STDOUT = None

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define LSK_ABI_VERSION 1
+#define LSK_ABI_VERSION 2
 #define LSK_MAX_SPEC 15      /* D_max: verify handles up to 16 rows (D+1)                    */
 #define LSK_MAX_EOS 8
 
@@ -36,8 +36,7 @@ typedef enum {
 #define LSK_FLAG_KEEP_LOGITS 1u  /* also store fp32 logits (needed for sampling / debug reads) */
 #define LSK_FLAG_NO_PDL 2u       /* disable programmatic dependent launch                    */
 #define LSK_FLAG_NO_GRAPH 4u     /* launch kernels eagerly instead of replaying CUDA graphs  */
-#define LSK_FLAG_MEGAKERNEL 8u   /* opt in: ONE persistent cooperative kernel per round / AR step     */
-#define LSK_FLAG_TP_ONESHOT 16u  /* opt in (tp_size > 1): one-shot collectives over peer-mapped HBM instead of NCCL */
+#define LSK_FLAG_TP_NCCL 16u     /* tp_size > 1: use NCCL all-reduce instead of the one-shot kernels over peer-mapped HBM */
 
 /* Llama architecture + engine sizing.  Replaces what the reference reads off the HF model
  * object (`model.config`, generate.py:54-67). */
@@ -48,7 +47,17 @@ typedef struct {
   int32_t tp_rank, tp_size;  /* tensor-parallel shard of this process (1 process per GPU)    */
   int32_t attn_splits;       /* split-KV factor (0 = default)                                */
   uint32_t flags;
+  /* RoPE frequency scaling (HF `rope_scaling` / `rope_parameters`, transformers
+   * modeling_rope_utils.py: _compute_linear_scaling_rope_parameters, _compute_llama3_parameters):
+   * 0 default, 1 linear (inv_freq / factor), 2 llama3 (Llama-3.1 / 3.2 checkpoints such as
+   * facebook/layerskip-llama3.2-1B, the reference's own test model, tests/tests_constants.py:9). */
+  int32_t rope_scaling;
+  float rope_factor, rope_low_freq_factor, rope_high_freq_factor;
+  int32_t rope_original_max_pos;
 } lsk_config;
+#define LSK_ROPE_DEFAULT 0
+#define LSK_ROPE_LINEAR 1
+#define LSK_ROPE_LLAMA3 2
 
 /* Which HF tensor a weight descriptor carries (names as in
  * transformers LlamaForCausalLM.state_dict(); call sites llama_model_utils.py:182,193,204-205). */
@@ -143,10 +152,15 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out);
 
 /* Queries / debugging (parity tests). */
 int lsk_kv_len(const lsk_engine* e, int32_t* len_out);
+/* Teacher-forced block: the m given ids as one block at positions kv_len .. kv_len+m-1 through
+ * every layer and the LM head — `forward` (llama_model_utils.py:155-209) on top of the committed
+ * context; logits of the m rows are then readable through LSK_DBG_LOGITS (needs
+ * LSK_FLAG_KEEP_LOGITS).  Nothing is committed. */
+int lsk_debug_forward_rows(lsk_engine* e, const int32_t* ids_host, int32_t m);
 typedef enum {
   LSK_DBG_HIDDEN = 0,        /* fp32 [16, hidden] residual-stream rows of the last launch     */
   LSK_DBG_LOGITS = 1,        /* fp32 [16, vocab_local] (needs LSK_FLAG_KEEP_LOGITS)           */
-  LSK_DBG_KROW = 2,          /* bf16->fp32 K cache row: layer, index = kv_head*max_ctx + pos  */
+  LSK_DBG_KROW = 2,          /* bf16->fp32 K cache row [head_dim]: layer, index = kv_head*max_ctx + pos */
   LSK_DBG_VROW = 3,
   LSK_DBG_PROBS_DRAFT = 4,   /* fp32 [16, vocab] warped (T, top-k, top-p) draft distributions     */
   LSK_DBG_PROBS_VERIFY = 5   /* fp32 [16, vocab] warped verifier distributions of the last round */
@@ -192,6 +206,14 @@ int lsk_plan_gemm(int64_t n_rows, int64_t k, int32_t m, int32_t pro, int32_t epi
 int lsk_test_pack(const void* w_bf16_dev, int64_t n, int64_t k, void* packed_out_dev);
 int lsk_test_gemm(const void* packed_dev, int64_t n, int64_t k, const void* x_bf16_dev,
                   int32_t m, float* y_dev, int32_t iters, float* avg_ms_out);
+/* Paged split-KV attention alone: m query rows at positions ctx-m .. ctx-1 attend causally to keys
+ * 0 .. ctx-1 (modeling_llama.py:187-221 eager attention).  q / out: [m][n_heads*head_dim] bf16,
+ * k / v: natural [n_kv_heads][ctx][head_dim] bf16 (k already rotated) — the entry point builds the
+ * engine's paged, swizzled pool from them; page_perm_host (nullable) permutes logical->physical
+ * pages.  All other pointers are device pointers. */
+int lsk_test_attn(const void* q_dev, const void* k_dev, const void* v_dev, int32_t n_heads,
+                  int32_t n_kv_heads, int32_t head_dim, int32_t ctx, int32_t m, int32_t n_splits,
+                  const int32_t* page_perm_host, void* out_dev, int32_t iters, float* avg_ms_out);
 /* tcgen05 LM head (csrc/lmhead_tc.cuh, opt-in): logits[m, n] = rmsnorm(x)[m, :] . W[n, :] with
  * W natural bf16 [n, k], x fp32 [m, k], norm_w bf16 [k]; writes fp32 logits [m, n] and per row the
  * arg-max (lowest index wins).  All pointers are device pointers. */

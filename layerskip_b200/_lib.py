@@ -16,8 +16,8 @@ LSK_MAX_EOS = 8
 LSK_FLAG_KEEP_LOGITS = 1
 LSK_FLAG_NO_PDL = 2
 LSK_FLAG_NO_GRAPH = 4
-LSK_FLAG_MEGAKERNEL = 8
-LSK_FLAG_TP_ONESHOT = 16
+LSK_FLAG_TP_NCCL = 16
+LSK_ROPE_DEFAULT, LSK_ROPE_LINEAR, LSK_ROPE_LLAMA3 = 0, 1, 2
 
 (LSK_W_EMBED, LSK_W_FINAL_NORM, LSK_W_LM_HEAD, LSK_W_LN1, LSK_W_Q, LSK_W_K, LSK_W_V, LSK_W_O,
  LSK_W_LN2, LSK_W_GATE, LSK_W_UP, LSK_W_DOWN) = range(12)
@@ -41,7 +41,10 @@ class lsk_config(C.Structure):
                 ("n_layers", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32),
                 ("head_dim", C.c_int32), ("rms_eps", C.c_float), ("rope_theta", C.c_float),
                 ("max_ctx", C.c_int32), ("tp_rank", C.c_int32), ("tp_size", C.c_int32),
-                ("attn_splits", C.c_int32), ("flags", C.c_uint32)]
+                ("attn_splits", C.c_int32), ("flags", C.c_uint32),
+                ("rope_scaling", C.c_int32), ("rope_factor", C.c_float),
+                ("rope_low_freq_factor", C.c_float), ("rope_high_freq_factor", C.c_float),
+                ("rope_original_max_pos", C.c_int32)]
 
 
 class lsk_weight_desc(C.Structure):
@@ -85,6 +88,7 @@ SIGNATURES = {
     "lsk_round": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(lsk_round_out)]),
     "lsk_ar_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "lsk_kv_len": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "lsk_debug_forward_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
     "lsk_debug_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                  C.POINTER(C.c_float), C.c_int64]),
     "lsk_debug_set_page_table": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
@@ -100,6 +104,9 @@ SIGNATURES = {
     "lsk_test_pack": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "lsk_test_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
+    "lsk_test_attn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                C.c_int32, C.POINTER(C.c_float)]),
     "lsk_test_lmhead_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int32, C.POINTER(C.c_float)]),

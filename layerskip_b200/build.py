@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "liblsk.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".liblsk.stamp")
 SOURCES = ["engine.cu"]
 HEADERS = ["common.cuh", "gemm_skinny.cuh", "attention.cuh", "misc_kernels.cuh", "sampling.cuh",
-           "megakernel.cuh", "tp_peer.cuh", "lmhead_tc.cuh",
+           "tp_peer.cuh", "lmhead_tc.cuh",
            os.path.join("..", "..", "include", "lsk.h")]
 
 NVCC_FLAGS = [

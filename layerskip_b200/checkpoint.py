@@ -22,7 +22,7 @@ from typing import Dict, Iterable, Iterator, List, Optional, Tuple
 import torch
 
 from . import _lib
-from .weights import LlamaArch, classify
+from .weights import LlamaArch, classify, parse_rope
 
 SAFETENSORS_INDEX = "model.safetensors.index.json"
 SAFETENSORS_SINGLE = "model.safetensors"
@@ -46,19 +46,14 @@ def arch_from_config_json(cfg: Dict) -> Tuple[LlamaArch, bool]:
     heads = int(cfg["num_attention_heads"])
     hidden = int(cfg["hidden_size"])
     head_dim = int(cfg.get("head_dim") or hidden // heads)
-    theta = cfg.get("rope_theta")
-    for key in ("rope_parameters", "rope_scaling"):
-        rp = cfg.get(key)
-        if isinstance(rp, dict):
-            kind = rp.get("rope_type", rp.get("type", "default"))
-            if kind not in ("default", None):
-                raise CheckpointError(f"rope scaling {kind!r} is not supported")
-            theta = rp.get("rope_theta", theta)
+    try:
+        rope = parse_rope(cfg.get)
+    except NotImplementedError as exc:
+        raise CheckpointError(str(exc)) from exc
     arch = LlamaArch(vocab=int(cfg["vocab_size"]), hidden=hidden,
                      inter=int(cfg["intermediate_size"]), layers=int(cfg["num_hidden_layers"]),
                      heads=heads, kv_heads=int(cfg.get("num_key_value_heads") or heads),
-                     head_dim=head_dim, rms_eps=float(cfg.get("rms_norm_eps", 1e-5)),
-                     rope_theta=float(theta if theta is not None else 10000.0))
+                     head_dim=head_dim, rms_eps=float(cfg.get("rms_norm_eps", 1e-5)), **rope)
     return arch, bool(cfg.get("tie_word_embeddings", False))
 
 
@@ -68,7 +63,8 @@ def config_json_of(arch: LlamaArch, tie_word_embeddings: bool = False) -> Dict:
         "vocab_size": arch.vocab, "hidden_size": arch.hidden, "intermediate_size": arch.inter,
         "num_hidden_layers": arch.layers, "num_attention_heads": arch.heads,
         "num_key_value_heads": arch.kv_heads, "head_dim": arch.head_dim,
-        "rms_norm_eps": arch.rms_eps, "rope_theta": arch.rope_theta, "hidden_act": "silu",
+        "rms_norm_eps": arch.rms_eps, "rope_theta": arch.rope_theta,
+        "rope_scaling": arch.rope_config(), "hidden_act": "silu",
         "attention_bias": False, "mlp_bias": False, "tie_word_embeddings": tie_word_embeddings,
         "torch_dtype": "bfloat16", "max_position_embeddings": 4096,
     }
@@ -188,7 +184,7 @@ class CheckpointLlama:
             vocab_size=a.vocab, hidden_size=a.hidden, intermediate_size=a.inter,
             num_hidden_layers=a.layers, num_attention_heads=a.heads,
             num_key_value_heads=a.kv_heads, head_dim=a.head_dim, rms_norm_eps=a.rms_eps,
-            rope_theta=a.rope_theta))()
+            rope_theta=a.rope_theta, rope_scaling=a.rope_config()))()
 
     def plan(self) -> List[Tuple[str, str]]:
         """(shard file, tensor name) in an order that opens every shard exactly once."""

@@ -7,7 +7,7 @@
 namespace lsk {
 
 constexpr int kPageTokens = 64;    // tokens per KV page
-constexpr int kHeadDim = 128;      // the kernels are specialised for head_dim 128
+constexpr int kMaxHeadDim = 128;   // head_dim in {32, 64, 128} (attention / RoPE epilogue are templated / parameterised)
 constexpr int kMaxRows = 16;       // rows (tokens) one step can carry: D_max + 1
 
 // ---------------------------------------------------------------------------------------
@@ -21,6 +21,38 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+
+// ---- mbarrier + TMA bulk copy (1-D cp.async.bulk, global -> shared, mbarrier completion)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 
 // streaming 128-bit load of packed weights: read-only path, do not allocate in L1.
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -65,6 +97,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 // arg-max with the "lowest index wins ties" rule used everywhere in the engine.
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
   return (v > bv) || (v == bv && i < bi);
+}
+
+// ---------------------------------------------------------------------------------------
+// KV pool layout: [layer][page][kv_head][64 tokens][head_dim] bf16.  Inside a token row the
+// 16-byte chunks are XOR-swizzled so that a whole (page, kv head) block can be moved into shared
+// memory by ONE TMA bulk copy and still be read conflict-free by the attention kernel's
+// fragment loads / ldmatrix (8 rows x one 16-byte chunk per access phase): rows of >= 128 bytes
+// (head_dim >= 64) use tok & 7, head_dim 32 (two rows per 128 bytes) uses (tok >> 1) & 3.
+// Every reader and writer of the pool goes through these two functions.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int kv_chunk_swizzle(int hd, int tok) {
+  return hd >= 64 ? (tok & 7) : ((tok >> 1) & 3);
+}
+__host__ __device__ __forceinline__ size_t kv_elem_offset(int hd, int page, int n_kv_heads, int head,
+                                                         int tok, int d) {
+  const int chunk = (d >> 3) ^ kv_chunk_swizzle(hd, tok);
+  return ((size_t)(page * n_kv_heads + head) * kPageTokens + tok) * hd + chunk * 8 + (d & 7);
 }
 
 // Device-resident generation state (one per engine).  `tok[0]` is the pending input token,

@@ -21,7 +21,6 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm_skinny.cuh"
-#include "megakernel.cuh"
 #include "tp_peer.cuh"
 #include "lmhead_tc.cuh"
 #include "misc_kernels.cuh"
@@ -88,7 +87,7 @@ struct lsk_engine {
   int sm_count = 0;
   // local (tensor-parallel shard) dimensions
   int heads_l = 0, kv_heads_l = 0, q_rows = 0, kv_rows = 0, inter_l = 0, vocab_l = 0,
-      vocab_l_pad = 0, vocab_off = 0, group = 0;
+      vocab_l_pad = 0, vocab_off = 0, group = 0, inter_l_pad = 0;
   int n_pages = 0, max_pos = 0, n_splits = 0;
   int max_rows = kMaxRows;             // token rows one step can carry (8 when 16 do not fit)
   bool use_pdl = true, use_graph = true, keep_logits = false;
@@ -126,9 +125,6 @@ struct lsk_engine {
   int* gath_idx = nullptr;
   float* rank_val = nullptr;           // TP: [16]
   int* rank_idx = nullptr;
-  float* part_o = nullptr;
-  float* part_ml = nullptr;
-  int* tickets = nullptr;
   int* d_zero = nullptr;
   int* d_prompt = nullptr;             // [max_ctx] prompt ids
   DevState* state = nullptr;
@@ -161,21 +157,6 @@ struct lsk_engine {
   int64_t capture_launches = 0;        // launches recorded while capturing the current graph
   std::map<long long, int64_t> graph_launches;
   float last_ms = 0.f;
-  // step megakernel: when `recording` is set the enqueue_* helpers append stage descriptors
-  // instead of launching kernels; programs live in device memory, one per graph key
-  bool use_mega = false;               // opt-in (LSK_FLAG_MEGAKERNEL / LSK_MEGA=1): measured slower, see DESIGN.md
-  bool attn_cluster = true;            // attention: cluster launch + DSMEM merge of the splits
-  bool attn_push = false;              // LSK_ATTN_PUSH=1: push-merge variant (one cluster barrier), unrun
-  int mega_ring = 6;                   // ring stages of the megakernel (96 KiB)
-  std::vector<StageDesc>* recording = nullptr;
-  bool record_failed = false;
-  std::map<long long, StageDesc*> programs;
-  std::map<long long, int> program_len;
-  unsigned int* grid_counter = nullptr;
-  unsigned long long* timeline = nullptr;   // LSK_MEGA_TIMELINE=1: per-stage start times (CTA 0)
-  std::map<long long, std::vector<int>> program_kinds;
-  double tl_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long tl_rounds = 0;
   // per-kernel-class timing (lsk_profile_round): events around every launch, eager mode
   bool profiling = false;
   int cur_class = 0;
@@ -234,9 +215,8 @@ struct GemmSched {
   size_t smem = 0;
   bool ok = false;
 };
-// fixed_ring == 0: stand-alone kernel, ring as deep as shared memory allows.
-// fixed_ring  > 0: megakernel stage, the scratch layout must fit behind a ring of that depth.
-static GemmSched plan_sched(int NT, int M, int pro, int epi, const GemmPlan& p, int sm_count, int fixed_ring = 0) {
+static GemmSched plan_sched(int NT, int M, int pro, int epi, const GemmPlan& p, int sm_count) {
+  constexpr int fixed_ring = 0;
   GemmSched best;
   for (int want = 1; want <= 16; ++want) {
     if (pro == PRO_RMS && want > 1) break;          // RMSNorm needs the whole row resident
@@ -307,18 +287,6 @@ static int launch_gemm_t(lsk_engine* e, const GemmPlan& p, GemmArgs& a) {
 template <int PRO, int EPI>
 static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
   const int NT = a.M <= 8 ? 1 : 2;
-  if (e->recording) {               // megakernel program: describe the stage instead of launching
-    const GemmSched sc = plan_sched(NT, a.M, PRO, EPI, p, e->sm_count, e->mega_ring);
-    if (!sc.ok) { e->record_failed = true; return LSK_OK; }
-    StageDesc d{};
-    d.kind = ST_GEMM; d.nt = NT; d.pro = PRO; d.epi = EPI; d.barrier_before = 1;
-    a.n_tiles = p.n_tiles; a.nsb = p.nsb; a.K = p.K;
-    a.tiles_per_pass = sc.tpp; a.n_chunks = sc.n_chunks; a.kc_sbs = sc.kc_sbs; a.n_stages = e->mega_ring; a.xs_rows = a.M;
-    a.next_W = nullptr; a.next_bytes = 0;
-    d.g = a;
-    e->recording->push_back(d);
-    return LSK_OK;
-  }
   if (NT == 1) return launch_gemm_t<1, PRO, EPI>(e, p, a);
   if (plan_sched(2, a.M, PRO, EPI, p, e->sm_count).ok) return launch_gemm_t<2, PRO, EPI>(e, p, a);
   return fail(LSK_ERR_INVALID, "%d token rows need the 16-row kernel, which does not fit next to K=%d "
@@ -326,11 +294,17 @@ static int launch_gemm(lsk_engine* e, const GemmPlan& p, GemmArgs a) {
 }
 
 // Tensor parallel: x[0..M) += sum over ranks of tp_buf (the fp32 partial of a row-parallel GEMM).
-// Default: NCCL all-reduce + residual add.  Opt-in (tp_peer.cuh): ONE kernel that pushes the
-// partial to every peer over NVLink, waits for theirs and adds the rank-ordered sum.
+// Peer mode 1 (default, tp_peer.cuh): ONE kernel pushes the partial to every peer over NVLink as
+// LL lines (flag inside the data), polls theirs and adds the rank-ordered sum to the residual.
+// Peer mode 3: the fence + flag protocol (A/B).  Without peer access: NCCL all-reduce + residual add,
+// timed by its own event pair so that `comm` never reads 0.
+static int ll_grid(int n2) {
+  int g = (n2 + kArThreads - 1) / kArThreads;
+  return g < 1 ? 1 : (g > 148 ? 148 : g);      // every CTA resident at once (spin-wait safety)
+}
 static int emit_allreduce_resid(lsk_engine* e, float* x, int M) {
   const lsk_config& c = e->cfg;
-  if (e->peer_ok) {
+  if (e->peer_ok && e->peer_mode == 3) {
     e->cur_class = CLS_COMM;
     const int n4 = M * c.hidden / 4;
     const int grid = (n4 + kArVecPerCta - 1) / kArVecPerCta;      // <= kMaxArCtas (hidden <= 8192)
@@ -338,22 +312,39 @@ static int emit_allreduce_resid(lsk_engine* e, float* x, int M) {
               (const float*)e->tp_buf, x, n4));
     return LSK_OK;
   }
+  if (e->peer_ok) {
+    e->cur_class = CLS_COMM;
+    const int n2 = M * c.hidden / 2;
+    CU(launch(e, tp_allreduce_ll_kernel, dim3(ll_grid(n2)), dim3(kArThreads), 0, e->peer,
+              (const float*)e->tp_buf, x, n2));
+    return LSK_OK;
+  }
   e->cur_class = CLS_COMM;
+  cudaEvent_t ea = nullptr, eb = nullptr;
+  if (e->profiling) {
+    cudaEventCreate(&ea); cudaEventCreate(&eb);
+    cudaEventRecord(ea, e->stream);
+  }
+  e->launches += 1;
+  e->capture_launches += 1;
   NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+  if (e->profiling) {
+    cudaEventRecord(eb, e->stream);
+    e->prof_events.push_back({CLS_COMM, {ea, eb}});
+  }
   e->cur_class = CLS_MISC;
   CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
   return LSK_OK;
 }
 
 // Fused variant (peer_mode 2): the row-parallel GEMM pushes its tiles to every rank from its
-// epilogue (gemm_skinny_push_kernel), a small kernel waits for all ranks' CTAs and adds the
-// rank-ordered sum to the residual rows.
+// epilogue as LL lines while it is still streaming weights (gemm_skinny_push_kernel); a small
+// kernel polls the lines of all ranks and adds the rank-ordered sum to the residual rows.
 static int emit_gemm_push_resid(lsk_engine* e, const GemmPlan& p, GemmArgs a, float* x) {
   const lsk_config& c = e->cfg;
   const int NT = a.M <= 8 ? 1 : 2;
   const GemmSched sc = plan_sched(NT, a.M, PRO_BF16, EPI_PUSH, p, e->sm_count);
   if (!sc.ok) return fail(LSK_ERR_INVALID, "skinny GEMM does not fit shared memory (K=%d, NT=%d)", p.K, NT);
-  if (sc.grid > kMaxGemmCtas) return fail(LSK_ERR_INVALID, "GEMM grid %d exceeds the peer flag array", sc.grid);
   a.n_tiles = p.n_tiles; a.nsb = p.nsb; a.K = p.K;
   a.tiles_per_pass = sc.tpp; a.n_chunks = sc.n_chunks; a.kc_sbs = sc.kc_sbs; a.n_stages = sc.n_stages;
   a.xs_rows = a.M;
@@ -369,10 +360,63 @@ static int emit_gemm_push_resid(lsk_engine* e, const GemmPlan& p, GemmArgs a, fl
   if (NT == 1) CU(launch(e, gemm_skinny_push_kernel<1>, dim3(sc.grid), dim3(kGemmThreads), sc.smem, a, e->peer));
   else CU(launch(e, gemm_skinny_push_kernel<2>, dim3(sc.grid), dim3(kGemmThreads), sc.smem, a, e->peer));
   e->cur_class = CLS_COMM;
-  const int n4 = a.M * c.hidden / 4;
-  const int grid = (n4 + kArVecPerCta - 1) / kArVecPerCta;
-  CU(launch(e, tp_finish_resid_kernel, dim3(grid), dim3(kArThreads), 0, e->peer, x, n4, sc.grid));
+  const int n2 = a.M * c.hidden / 2;
+  CU(launch(e, tp_finish_ll_kernel, dim3(ll_grid(n2)), dim3(kArThreads), 0, e->peer, x, n2));
   return LSK_OK;
+}
+
+// Attention over the paged cache: the splits of one kv head = one thread-block cluster (DSMEM
+// merge); head_dim selects the instantiation, the shared-memory plan depends on (group, M).
+template <int HD>
+static int launch_attention_t(lsk_engine* e, AttnArgs& a) {
+  static std::atomic<uint64_t> configured{0};
+  auto kern = attn_cluster_kernel<HD>;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_relaxed) & bit)) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured.fetch_or(bit, std::memory_order_relaxed);
+  }
+  const AttnSmemPlan sp = attn_smem_plan(HD, a.group, a.M);
+  if (sp.total > (size_t)kSmemMax)
+    return fail(LSK_ERR_INVALID, "attention: %d query rows per kv head do not fit shared memory", a.group * a.M);
+  a.rows_pad = (a.group * a.M + 15) / 16 * 16;
+  a.merge_off = sp.merge_off; a.part_off = sp.part_off; a.reload_per_rb = sp.reload_per_rb;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.n_kv_heads, a.n_splits);
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = sp.total;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = a.n_splits; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = e->use_pdl ? 2 : 1;
+  e->launches += 1;
+  e->capture_launches += 1;
+  if (!e->profiling) {
+    CU(cudaLaunchKernelEx(&cfg, kern, a));
+  } else {
+    cudaEvent_t ea, eb;
+    cudaEventCreate(&ea); cudaEventCreate(&eb);
+    cudaEventRecord(ea, e->stream);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, a);
+    cudaEventRecord(eb, e->stream);
+    e->prof_events.push_back({e->cur_class, {ea, eb}});
+    CU(err);
+  }
+  return LSK_OK;
+}
+static int launch_attention(lsk_engine* e, AttnArgs& a, int head_dim) {
+  switch (head_dim) {
+    case 128: return launch_attention_t<128>(e, a);
+    case 64: return launch_attention_t<64>(e, a);
+    case 32: return launch_attention_t<32>(e, a);
+    default: return fail(LSK_ERR_INVALID, "head_dim %d unsupported (32, 64 or 128)", head_dim);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,7 +442,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.x_f32 = x; a.x_ld = c.hidden; a.norm_w = L.ln1; a.eps = c.rms_eps;
     a.q_out = e->qbuf; a.q_ld = e->q_rows;
     a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
-    a.base_len = base_len; a.pos_off = pos_off; a.rope = e->rope;
+    a.base_len = base_len; a.pos_off = pos_off; a.rope = e->rope; a.head_dim = c.head_dim;
     a.q_rows = e->q_rows; a.kv_rows = e->kv_rows; a.n_kv_heads = e->kv_heads_l;
     a.next_W = L.wo; a.next_bytes = e->l2_prefetch_bytes ? (size_t)e->q_rows * h2 : 0;
     TRY((launch_gemm<PRO_RMS, EPI_QKV>(e, e->p_qkv, a)));
@@ -411,44 +455,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.base_len = base_len; a.pos_off = pos_off; a.M = M; a.group = e->group;
     a.n_kv_heads = e->kv_heads_l; a.n_splits = e->n_splits;
     a.scale = 1.0f / sqrtf((float)c.head_dim);
-    a.part_o = e->part_o; a.part_ml = e->part_ml; a.rows_pad = e->group * 16;
-    a.tickets = e->tickets; a.n_pages = e->n_pages;
-    if (e->recording) {
-      StageDesc d{};
-      d.kind = ST_ATTN; d.barrier_before = 1; d.a = a;
-      e->recording->push_back(d);
-    } else if (e->attn_cluster) {
-      // the splits of one kv head = one thread-block cluster (DSMEM merge)
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(e->kv_heads_l, e->n_splits);
-      cfg.blockDim = dim3(kAttnThreads);
-      cfg.dynamicSmemBytes = e->attn_push ? attn_push_smem_bytes(a.rows_pad)
-                                          : kAttnTeamSmem + (size_t)a.rows_pad * (kHeadDim + 2) * 4;
-      auto attn_kernel = e->attn_push ? attn_cluster_push_kernel : attn_cluster_kernel;
-      cfg.stream = e->stream;
-      cudaLaunchAttribute at[2];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = e->n_splits; at[0].val.clusterDim.z = 1;
-      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[1].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = e->use_pdl ? 2 : 1;
-      e->launches += 1;
-      e->capture_launches += 1;
-      if (!e->profiling) {
-        CU(cudaLaunchKernelEx(&cfg, attn_kernel, a));
-      } else {
-        cudaEvent_t ea, eb;
-        cudaEventCreate(&ea); cudaEventCreate(&eb);
-        cudaEventRecord(ea, e->stream);
-        cudaError_t err = cudaLaunchKernelEx(&cfg, attn_kernel, a);
-        cudaEventRecord(eb, e->stream);
-        e->prof_events.push_back({e->cur_class, {ea, eb}});
-        CU(err);
-      }
-    } else {
-      CU(launch(e, attn_splitkv_kernel, dim3(e->kv_heads_l, e->n_splits), dim3(kAttnThreads), 0, a));
-    }
+    TRY(launch_attention(e, a, c.head_dim));
   }
   if (!(e->ablate & (1u << CLS_O))) {  // O projection (+ residual, or all-reduce then residual under TP)
     e->cur_class = CLS_O;
@@ -474,7 +481,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     a.W = reinterpret_cast<const uint4*>(L.wgu);
     a.M = M;
     a.x_f32 = x; a.x_ld = c.hidden; a.norm_w = L.ln2; a.eps = c.rms_eps;
-    a.act = e->act; a.act_ld = e->inter_l;
+    a.act = e->act; a.act_ld = e->inter_l_pad;
     a.next_W = L.wd; a.next_bytes = cap((size_t)e->inter_l * h2);
     TRY((launch_gemm<PRO_RMS, EPI_SILU>(e, e->p_gu, a)));
   }
@@ -483,7 +490,7 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
     GemmArgs a{};
     a.W = reinterpret_cast<const uint4*>(L.wd);
     a.M = M;
-    a.x_bf16 = e->act; a.xb_ld = e->inter_l;
+    a.x_bf16 = e->act; a.xb_ld = e->inter_l_pad;
     a.next_W = after_W; a.next_bytes = after_W ? cap(after_bytes) : 0;
     if (!tp) {
       a.out_f32 = x; a.out_ld = c.hidden;
@@ -500,19 +507,11 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
 }
 
 // ---------------------------------------------------------------------------------------------
-// small stages: launched as kernels, or recorded into a megakernel program
+// small stages
 // ---------------------------------------------------------------------------------------------
 static int emit_embed(lsk_engine* e, const int* ids, float* rows, int n_rows) {
   const lsk_config& c = e->cfg;
   e->cur_class = CLS_MISC;
-  if (e->recording) {
-    StageDesc d{};
-    d.kind = ST_EMBED; d.barrier_before = 1;
-    d.m.embed = e->embed; d.m.hidden = c.hidden; d.m.ids = ids; d.m.rows = rows; d.m.row_ld = c.hidden;
-    d.m.n_rows = n_rows;
-    e->recording->push_back(d);
-    return LSK_OK;
-  }
   CU(launch(e, embed_tokens_kernel, dim3(n_rows), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
             ids, rows, c.hidden));
   return LSK_OK;
@@ -526,42 +525,18 @@ static int n_cand(lsk_engine* e);
 static int emit_finalize(lsk_engine* e, int slot, float* dst_row) {
   const lsk_config& c = e->cfg;
   e->cur_class = CLS_MISC;
-  if (e->recording) {
-    StageDesc d{};
-    d.kind = ST_FINALIZE; d.barrier_before = 1;
-    d.m.cand_val = e->cand_val; d.m.cand_idx = e->cand_idx; d.m.n_cand = e->sm_count;
-    d.m.st = e->state; d.m.slot = slot; d.m.embed = e->embed; d.m.hidden = c.hidden; d.m.dst_row = dst_row;
-    e->recording->push_back(d);
-    return LSK_OK;
-  }
   CU(launch(e, finalize_embed_kernel, dim3(8), dim3(128), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e),
             e->state, slot, (const __nv_bfloat16*)e->embed, c.hidden, dst_row));
   return LSK_OK;
 }
 static int emit_accept(lsk_engine* e, int d_spec, int seq) {
   e->cur_class = CLS_MISC;
-  if (e->recording) {
-    StageDesc d{};
-    d.kind = ST_ACCEPT; d.barrier_before = 1;
-    d.m.cand_val = e->cand_val; d.m.cand_idx = e->cand_idx; d.m.n_cand = e->sm_count;
-    d.m.st = e->state; d.m.d = d_spec; d.m.gp = e->gen_dev; d.m.res = e->res_dev;
-    e->recording->push_back(d);
-    return LSK_OK;
-  }
   CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d_spec,
             e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
   return LSK_OK;
 }
 static int emit_ar_commit(lsk_engine* e, int seq) {
   e->cur_class = CLS_MISC;
-  if (e->recording) {
-    StageDesc d{};
-    d.kind = ST_AR_COMMIT; d.barrier_before = 1;
-    d.m.cand_val = e->cand_val; d.m.cand_idx = e->cand_idx; d.m.n_cand = e->sm_count;
-    d.m.st = e->state; d.m.res = e->res_dev;
-    e->recording->push_back(d);
-    return LSK_OK;
-  }
   CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
             e->res_dev, seq));
   return LSK_OK;
@@ -583,7 +558,7 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
   a.part_val = e->cand_val; a.part_idx = e->cand_idx;
   a.next_W = after_W;
   a.next_bytes = after_W ? (after_bytes < e->l2_prefetch_bytes ? after_bytes : e->l2_prefetch_bytes) : 0;
-  if (e->lm_tc && !e->recording) {
+  if (e->lm_tc) {
     if (!(e->ablate & (1u << CLS_LMHEAD))) {
       LmHeadTcArgs t{};
       t.W = e->lm_head_tc; t.n_tiles = e->lm_tc_tiles; t.K = c.hidden; t.M = M; t.n_stages = e->lm_tc_stages;
@@ -733,92 +708,6 @@ static int run_cached(lsk_engine* e, long long key, F enqueue) {
   return LSK_OK;
 }
 
-// Megakernel path: record the stage program once per key, then replay
-//   memset(grid barrier counter) -> ONE cooperative launch of step_megakernel.
-// Returns 1 when the shape cannot be served by the megakernel (caller falls back).
-template <typename F>
-static int run_mega(lsk_engine* e, long long key, F enqueue) {
-  auto pit = e->programs.find(key);
-  if (pit == e->programs.end()) {
-    std::vector<StageDesc> prog;
-    e->recording = &prog;
-    e->record_failed = false;
-    int st = enqueue();
-    e->recording = nullptr;
-    if (st != LSK_OK) return st;
-    if (e->record_failed || prog.empty()) {
-      e->programs[key] = nullptr;
-      e->program_len[key] = 0;
-      return 1;
-    }
-    prog[0].barrier_before = 0;
-    StageDesc* dev = nullptr;
-    CU(cudaMalloc((void**)&dev, prog.size() * sizeof(StageDesc)));
-    CU(cudaMemcpy(dev, prog.data(), prog.size() * sizeof(StageDesc), cudaMemcpyHostToDevice));
-    e->programs[key] = dev;
-    e->program_len[key] = (int)prog.size();
-    {
-      std::vector<int> kinds;
-      for (auto& d : prog) kinds.push_back(d.kind == ST_GEMM ? 10 + d.epi : d.kind);
-      e->program_kinds[key] = kinds;
-    }
-    pit = e->programs.find(key);
-  }
-  if (pit->second == nullptr) return 1;
-  StageDesc* dev = pit->second;
-  const int n = e->program_len[key];
-  const int rc = run_cached(e, key | (1LL << 40), [&]() -> int {
-    CU(cudaMemsetAsync(e->grid_counter, 0, sizeof(unsigned int), e->stream));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(e->sm_count);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = kSmemMax;
-    cfg.stream = e->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = getenv("LSK_MEGA_NO_COOP") ? 0 : 1;
-    e->launches += 1;
-    e->capture_launches += 1;
-    CU(cudaLaunchKernelEx(&cfg, step_megakernel, (const StageDesc*)dev, n, e->grid_counter, e->mega_ring,
-                          e->timeline));
-    return LSK_OK;
-  });
-  if (rc == LSK_OK && e->timeline && n < 4096) {
-    std::vector<unsigned long long> t(n + 1);
-    CU(cudaMemcpy(t.data(), e->timeline, (n + 1) * 8, cudaMemcpyDeviceToHost));
-    const std::vector<int>& kinds = e->program_kinds[key];
-    for (int i = 0; i < n; ++i) {
-      const int k = kinds[i];
-      const int slot = k >= 10 ? (k - 10 + 3) : (k == ST_ATTN ? 1 : 2);   // 1 attn, 2 small, 3.. gemm by epilogue
-      e->tl_ns[slot & 7] += (double)(t[i + 1] - t[i]);
-    }
-    e->tl_rounds += 1;
-    if (getenv("LSK_MEGA_PHASES") && e->tl_rounds == 8) {   // one detailed dump (SM-clock cycles)
-      std::vector<unsigned long long> ph((size_t)4 * 4096 * 4);
-      CU(cudaMemcpy(ph.data(), e->timeline + 4097, ph.size() * 8, cudaMemcpyDeviceToHost));
-      const int ctas[4] = {0, 27, 100, e->sm_count - 1};
-      fprintf(stderr, "[lsk phases] stage kind | per CTA: prologue, consume, cta-done wait, barrier wait (cycles)\n");
-      for (int i = 0; i < n && i < 48; ++i) {
-        fprintf(stderr, "  s%02d k%02d |", i, kinds[i]);
-        for (int cs = 0; cs < 4; ++cs) {
-          const unsigned long long* a = &ph[((size_t)cs * 4096 + i) * 4];
-          const unsigned long long* nx = &ph[((size_t)cs * 4096 + i + 1) * 4];
-          if (kinds[i] >= 10)
-            fprintf(stderr, " c%03d: %6lld %6lld %6lld %6lld |", ctas[cs], (long long)(a[1] - a[0]),
-                    (long long)(a[2] - a[1]), (long long)(a[3] - a[2]), (long long)(nx[0] - a[3]));
-          else
-            fprintf(stderr, " c%03d: %6s %6lld %6s %6lld |", ctas[cs], "-", (long long)(a[3] - a[0]), "-",
-                    (long long)(nx[0] - a[3]));
-        }
-        fprintf(stderr, "\n");
-      }
-    }
-  }
-  return rc;
-}
-
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -832,11 +721,19 @@ static int create_into(lsk_engine* e, const lsk_config& c);
 int lsk_create(const lsk_config* cfg, lsk_engine** out) {
   if (!cfg || !out) return fail(LSK_ERR_INVALID, "null argument");
   const lsk_config& c = *cfg;
-  if (c.head_dim != kHeadDim) return fail(LSK_ERR_INVALID, "head_dim %d unsupported (kernels are specialised for 128)", c.head_dim);
+  if (c.head_dim != 128 && c.head_dim != 64 && c.head_dim != 32)
+    return fail(LSK_ERR_INVALID, "head_dim %d unsupported (32, 64 or 128)", c.head_dim);
+  if (c.rope_scaling < LSK_ROPE_DEFAULT || c.rope_scaling > LSK_ROPE_LLAMA3)
+    return fail(LSK_ERR_INVALID, "rope_scaling %d unknown", c.rope_scaling);
+  if (c.rope_scaling != LSK_ROPE_DEFAULT && !(c.rope_factor > 0.f))
+    return fail(LSK_ERR_INVALID, "rope scaling needs factor > 0");
+  if (c.rope_scaling == LSK_ROPE_LLAMA3 &&
+      (!(c.rope_high_freq_factor > c.rope_low_freq_factor) || c.rope_original_max_pos < 1))
+    return fail(LSK_ERR_INVALID, "llama3 rope scaling needs high_freq_factor > low_freq_factor and original_max_position_embeddings");
   if (c.tp_size < 1 || c.tp_rank < 0 || c.tp_rank >= c.tp_size) return fail(LSK_ERR_INVALID, "bad tp_rank/tp_size");
   if (c.n_heads % c.tp_size || c.n_kv_heads % c.tp_size || c.n_heads % c.n_kv_heads)
     return fail(LSK_ERR_INVALID, "heads (%d) / kv heads (%d) must divide by tp_size (%d)", c.n_heads, c.n_kv_heads, c.tp_size);
-  if (c.inter % (c.tp_size * 32)) return fail(LSK_ERR_INVALID, "intermediate size %d must be a multiple of 32*tp_size", c.inter);
+  if (c.inter % (c.tp_size * 8)) return fail(LSK_ERR_INVALID, "intermediate size %d must be a multiple of 8*tp_size", c.inter);
   if (c.hidden % 32 || c.hidden > 8192) return fail(LSK_ERR_INVALID, "hidden %d must be a multiple of 32 and <= 8192", c.hidden);
   if (c.vocab % c.tp_size) return fail(LSK_ERR_INVALID, "vocab must divide by tp_size");
   if (c.n_layers < 1 || c.max_ctx < 2) return fail(LSK_ERR_INVALID, "bad n_layers / max_ctx");
@@ -862,12 +759,15 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->use_pdl = !(c.flags & LSK_FLAG_NO_PDL);
   e->use_graph = !(c.flags & LSK_FLAG_NO_GRAPH);
   e->keep_logits = (c.flags & LSK_FLAG_KEEP_LOGITS) != 0;
-  e->use_mega = ((c.flags & LSK_FLAG_MEGAKERNEL) || getenv("LSK_MEGA")) && !getenv("LSK_NO_MEGA");
-  e->attn_cluster = !getenv("LSK_NO_ATTN_CLUSTER");
-  e->attn_push = e->attn_cluster && getenv("LSK_ATTN_PUSH") && atoi(getenv("LSK_ATTN_PUSH")) != 0;
-  e->want_peer = c.tp_size > 1 && ((c.flags & LSK_FLAG_TP_ONESHOT) ||
-                                   (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) != 0));
-  if (getenv("LSK_TP_ONESHOT") && atoi(getenv("LSK_TP_ONESHOT")) == 2) e->peer_mode = 2;
+  // tensor-parallel collectives: one-shot kernels over peer-mapped HBM by default
+  // (LSK_TP_ONESHOT: 0 = NCCL, 1 = LL push + reduce kernel, 2 = LL push fused into the GEMM epilogue,
+  //  3 = fence + flag protocol); LSK_FLAG_TP_NCCL forces NCCL from the API
+  {
+    const char* env = getenv("LSK_TP_ONESHOT");
+    const int mode = env ? atoi(env) : ((c.flags & LSK_FLAG_TP_NCCL) ? 0 : 1);
+    e->want_peer = c.tp_size > 1 && mode != 0;
+    e->peer_mode = (mode >= 1 && mode <= 3) ? mode : 1;
+  }
   if (const char* env = getenv("LSK_ABLATE")) {
     // diagnostics only: the named kernel classes are not launched (results are garbage, the
     // round keeps its shape) so that t(full) - t(ablated) gives a class's cost INSIDE the graph
@@ -882,13 +782,13 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
     }
     if (e->ablate) fprintf(stderr, "[lsk] LSK_ABLATE=%s: kernel classes skipped, outputs are NOT valid\n", env);
   }
-  if (const char* env = getenv("LSK_MEGA_RING")) { int v = atoi(env); if (v >= 3 && v <= kMaxStages) e->mega_ring = v; }
   e->heads_l = c.n_heads / c.tp_size;
   e->kv_heads_l = c.n_kv_heads / c.tp_size;
   e->group = c.n_heads / c.n_kv_heads;
-  e->q_rows = e->heads_l * kHeadDim;
-  e->kv_rows = e->kv_heads_l * kHeadDim;
+  e->q_rows = e->heads_l * c.head_dim;
+  e->kv_rows = e->kv_heads_l * c.head_dim;
   e->inter_l = c.inter / c.tp_size;
+  e->inter_l_pad = (e->inter_l + 31) / 32 * 32;   // K of the down projection (zero columns beyond inter_l)
   e->vocab_l = c.vocab / c.tp_size;
   e->vocab_l_pad = (e->vocab_l + 15) / 16 * 16;
   e->vocab_off = c.tp_rank * e->vocab_l;
@@ -905,7 +805,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->p_qkv = make_plan(e->q_rows + 2 * e->kv_rows, c.hidden, e->sm_count);
   e->p_o = make_plan(c.hidden, e->q_rows, e->sm_count);
   e->p_gu = make_plan(2 * e->inter_l, c.hidden, e->sm_count);
-  e->p_d = make_plan(c.hidden, e->inter_l, e->sm_count);
+  e->p_d = make_plan(c.hidden, e->inter_l_pad, e->sm_count);
   e->p_lm = make_plan(e->vocab_l_pad, c.hidden, e->sm_count);
   e->lm_cand = e->p_lm.n_tiles < e->sm_count ? e->p_lm.n_tiles : e->sm_count;
   if (const char* env = getenv("LSK_L2_PREFETCH_MB")) e->l2_prefetch_bytes = (size_t)atoi(env) << 20;
@@ -943,7 +843,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
     TRY(alloc((void**)&L.wqkv, (size_t)(e->q_rows + 2 * e->kv_rows) * h * 2));
     TRY(alloc((void**)&L.wo, h * e->q_rows * 2));
     TRY(alloc((void**)&L.wgu, (size_t)2 * e->inter_l * h * 2));
-    TRY(alloc((void**)&L.wd, h * e->inter_l * 2));
+    TRY(alloc((void**)&L.wd, h * e->inter_l_pad * 2));
     TRY(alloc((void**)&L.ln1, h * 2));
     TRY(alloc((void**)&L.ln2, h * 2));
   }
@@ -954,15 +854,15 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
     TRY(alloc((void**)&e->lm_head_tc, (size_t)e->lm_tc_tiles * kTcTileRows * h * 2));
     CU(cudaFuncSetAttribute(lmhead_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   }
-  e->pool_layer_elems = (size_t)e->n_pages * e->kv_heads_l * kPageTokens * kHeadDim;
+  e->pool_layer_elems = (size_t)e->n_pages * e->kv_heads_l * kPageTokens * c.head_dim;
   TRY(alloc((void**)&e->kpool, e->pool_layer_elems * c.n_layers * 2));
   TRY(alloc((void**)&e->vpool, e->pool_layer_elems * c.n_layers * 2));
   TRY(alloc((void**)&e->page_table, (size_t)e->n_pages * 4));
-  TRY(alloc((void**)&e->rope, (size_t)e->max_pos * 64 * sizeof(float2)));
+  TRY(alloc((void**)&e->rope, (size_t)e->max_pos * (c.head_dim / 2) * sizeof(float2)));
   TRY(alloc((void**)&e->hidden, (size_t)(kMaxRows + 1) * h * 4));
   TRY(alloc((void**)&e->qbuf, (size_t)kMaxRows * e->q_rows * 2));
   TRY(alloc((void**)&e->attn_out, (size_t)kMaxRows * e->q_rows * 2));
-  TRY(alloc((void**)&e->act, (size_t)kMaxRows * e->inter_l * 2));
+  TRY(alloc((void**)&e->act, (size_t)kMaxRows * e->inter_l_pad * 2));   // pad columns stay zero
   TRY(alloc((void**)&e->tp_buf, (size_t)kMaxRows * h * 4));
   if (e->keep_logits) TRY(alloc((void**)&e->logits, (size_t)kMaxRows * e->vocab_l_pad * 4));
   TRY(alloc((void**)&e->cand_val, (size_t)e->sm_count * kMaxRows * 4));
@@ -971,16 +871,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   TRY(alloc((void**)&e->gath_idx, (size_t)c.tp_size * kMaxRows * 4));
   TRY(alloc((void**)&e->rank_val, kMaxRows * 4));
   TRY(alloc((void**)&e->rank_idx, kMaxRows * 4));
-  const size_t prow = (size_t)e->kv_heads_l * e->n_splits * e->group * 16;
-  TRY(alloc((void**)&e->part_o, prow * kHeadDim * 4));
-  TRY(alloc((void**)&e->part_ml, prow * 2 * 4));
-  TRY(alloc((void**)&e->tickets, (size_t)e->kv_heads_l * 4));
   TRY(alloc((void**)&e->d_zero, 4));
-  TRY(alloc((void**)&e->grid_counter, 4));
-  if (getenv("LSK_MEGA_TIMELINE")) TRY(alloc((void**)&e->timeline, (4097 + 4 * 4096 * 4) * 8));
-  CU(cudaFuncSetAttribute(step_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-  CU(cudaFuncSetAttribute(attn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CU(cudaFuncSetAttribute(attn_cluster_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   TRY(alloc((void**)&e->d_prompt, (size_t)e->max_pos * 4));
   TRY(alloc((void**)&e->state, sizeof(DevState)));
   TRY(alloc((void**)&e->gen_dev, sizeof(GenParams)));
@@ -992,12 +883,29 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
     std::vector<int> pt(e->n_pages);
     for (int i = 0; i < e->n_pages; ++i) pt[i] = i;
     CU(cudaMemcpyAsync(e->page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, e->stream));
-    std::vector<float2> tab((size_t)e->max_pos * 64);
-    for (int d = 0; d < 64; ++d) {
-      const float inv_freq = 1.0f / powf(c.rope_theta, (float)(2 * d) / (float)kHeadDim);
+    // inv_freq as transformers computes it (modeling_rope_utils.py): default theta^(-2i/d), then the
+    // checkpoint's scaling rule; angle and cos/sin in fp32 like LlamaRotaryEmbedding.forward
+    const int half = c.head_dim / 2;
+    std::vector<float2> tab((size_t)e->max_pos * half);
+    for (int d = 0; d < half; ++d) {
+      float inv_freq = 1.0f / powf(c.rope_theta, (float)(2 * d) / (float)c.head_dim);
+      if (c.rope_scaling == LSK_ROPE_LINEAR) {
+        inv_freq /= c.rope_factor;
+      } else if (c.rope_scaling == LSK_ROPE_LLAMA3) {
+        const float old_len = (float)c.rope_original_max_pos;
+        const float low_wavelen = old_len / c.rope_low_freq_factor, high_wavelen = old_len / c.rope_high_freq_factor;
+        const float wavelen = 2.0f * (float)M_PI / inv_freq;
+        float scaled = wavelen > low_wavelen ? inv_freq / c.rope_factor : inv_freq;
+        if (!(wavelen < high_wavelen) && !(wavelen > low_wavelen)) {
+          const float smooth = (old_len / wavelen - c.rope_low_freq_factor) /
+                               (c.rope_high_freq_factor - c.rope_low_freq_factor);
+          scaled = (1.0f - smooth) * scaled / c.rope_factor + smooth * scaled;
+        }
+        inv_freq = scaled;
+      }
       for (int p = 0; p < e->max_pos; ++p) {
         const float ang = (float)p * inv_freq;
-        tab[(size_t)p * 64 + d] = make_float2((float)cos((double)ang), (float)sin((double)ang));
+        tab[(size_t)p * half + d] = make_float2((float)cos((double)ang), (float)sin((double)ang));
       }
     }
     CU(cudaMemcpyAsync(e->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
@@ -1014,21 +922,13 @@ void lsk_destroy(lsk_engine* e) {
   if (e->peer_region) cudaFree(e->peer_region);
   if (e->peer_err_host) cudaFreeHost(e->peer_err_host);
   if (e->comm) ncclCommDestroy(e->comm);
-  if (e->timeline && e->tl_rounds > 0) {
-    const char* names[8] = {"-", "attention", "small", "gemm_qkv", "gemm_resid(o+down)", "gemm_store", "gemm_silu", "gemm_lmhead"};
-    fprintf(stderr, "[lsk megakernel timeline] per round over %ld launches (stage = barrier-to-barrier on CTA 0):\n", e->tl_rounds);
-    for (int i = 1; i < 8; ++i) fprintf(stderr, "   %-20s %9.1f us\n", names[i], e->tl_ns[i] / e->tl_rounds / 1e3);
-    cudaFree(e->timeline);
-  }
-  for (auto& kv : e->programs) if (kv.second) cudaFree(kv.second);
-  if (e->grid_counter) cudaFree(e->grid_counter);
   for (auto& L : e->layers) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
   }
   void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->lm_head_tc, e->kpool, e->vpool, e->page_table, e->rope,
                   e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->logits_gath, e->logits_full, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
-                  e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx, e->part_o,
-                  e->part_ml, e->tickets, e->d_zero, e->d_prompt, e->state, e->gen_dev};
+                  e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx,
+                  e->d_zero, e->d_prompt, e->state, e->gen_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->res_host) cudaFreeHost(e->res_host);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1069,13 +969,18 @@ static int peer_setup(lsk_engine* e) {
   std::vector<cudaIpcMemHandle_t> all(tp);
   CU(cudaMemcpy(all.data(), d_h, hb * tp, cudaMemcpyDeviceToHost));
   cudaFree(d_h);
+  int local_ok = 1;
+  std::string why;
   for (int r = 0; r < tp; ++r) {
     if (r == rank) { e->peer.base[r] = (unsigned char*)e->peer_region; continue; }
     void* p = nullptr;
     cudaError_t er = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
-    if (er != cudaSuccess)
-      return fail(LSK_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s (one-shot TP collectives need "
-                  "one process per GPU with peer access)", r, cudaGetErrorString(er));
+    if (er != cudaSuccess) {
+      local_ok = 0;
+      why = cudaGetErrorString(er);
+      cudaGetLastError();
+      continue;
+    }
     e->peer_opened[r] = p;
     e->peer.base[r] = (unsigned char*)p;
   }
@@ -1085,10 +990,21 @@ static int peer_setup(lsk_engine* e) {
   e->peer.rank = rank;
   e->peer.size = tp;
   e->peer.hidden = e->cfg.hidden;
-  // nobody may push into a region before its owner has zeroed it: all did (they produced a handle),
-  // and this all-reduce keeps the ranks together until every mapping exists
-  NC(ncclAllReduce(e->tp_buf, e->tp_buf, 1, ncclFloat, ncclSum, e->comm, e->stream));
+  // every rank must take the same path: agree on min(local_ok).  The all-reduce also keeps the
+  // ranks together until every mapping exists (nobody pushes into a region before its owner has
+  // zeroed it: all did, they produced a handle).
+  const float mine_ok = (float)local_ok;
+  CU(cudaMemcpyAsync(e->tp_buf, &mine_ok, 4, cudaMemcpyHostToDevice, e->stream));
+  NC(ncclAllReduce(e->tp_buf, e->tp_buf, 1, ncclFloat, ncclMin, e->comm, e->stream));
+  float all_ok = 0.f;
+  CU(cudaMemcpyAsync(&all_ok, e->tp_buf, 4, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemsetAsync(e->tp_buf, 0, 4, e->stream));
+  if (all_ok < 0.5f) {
+    fprintf(stderr, "[lsk] rank %d: peer mapping unavailable (%s): tensor-parallel collectives fall back to NCCL\n",
+            rank, local_ok ? "another rank failed" : why.c_str());
+    return LSK_OK;
+  }
   e->peer_ok = true;
   return LSK_OK;
 }
@@ -1110,12 +1026,13 @@ int lsk_comm_init(lsk_engine* e, const uint8_t id_in[128]) {
 }
 
 static int pack(lsk_engine* e, const __nv_bfloat16* src, int64_t src_ld, int64_t row0, int64_t col0,
-                int64_t n_rows, int64_t K, __nv_bfloat16* dst, int64_t dst_row0, int mode) {
+                int64_t n_rows, int64_t K, __nv_bfloat16* dst, int64_t dst_row0, int mode, int64_t K_dst = 0) {
+  if (K_dst == 0) K_dst = K;
   const int64_t pairs = n_rows * (K / 2);
   int blocks = (int)((pairs + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
-  pack_rows_kernel<<<blocks, 256, 0, e->stream>>>(src, src_ld, row0, col0, n_rows, K, dst, dst_row0, mode);
+  pack_rows_kernel<<<blocks, 256, 0, e->stream>>>(src, src_ld, row0, col0, n_rows, K, dst, dst_row0, mode, K_dst, e->cfg.head_dim);
   CU(cudaGetLastError());
   return LSK_OK;
 }
@@ -1136,7 +1053,7 @@ int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n) {
     const bool per_layer = d.role >= LSK_W_LN1;
     if (per_layer && (d.layer < 0 || d.layer >= c.n_layers)) return fail(LSK_ERR_INVALID, "bad layer %d", d.layer);
     LayerWeights* L = per_layer ? &e->layers[d.layer] : nullptr;
-    const int64_t h = c.hidden, qd = (int64_t)c.n_heads * kHeadDim, kvd = (int64_t)c.n_kv_heads * kHeadDim;
+    const int64_t h = c.hidden, qd = (int64_t)c.n_heads * c.head_dim, kvd = (int64_t)c.n_kv_heads * c.head_dim;
     switch (d.role) {
       case LSK_W_EMBED:
         TRY(expect(c.vocab, h));
@@ -1192,7 +1109,7 @@ int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n) {
         break;
       case LSK_W_DOWN:
         TRY(expect(h, c.inter));
-        TRY(pack(e, src, c.inter, 0, (int64_t)r * e->inter_l, h, e->inter_l, L->wd, 0, MAP_PLAIN));
+        TRY(pack(e, src, c.inter, 0, (int64_t)r * e->inter_l, h, e->inter_l, L->wd, 0, MAP_PLAIN, e->inter_l_pad));
         break;
       default:
         return fail(LSK_ERR_INVALID, "unknown weight role %d", d.role);
@@ -1304,12 +1221,7 @@ int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
   if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context %d + %d exceeds max_ctx", e->host_len, d_req + 1);
   const int seq = ++e->seq;
   const long long key = ((long long)E << 20) | ((long long)d_req << 8) | (e->gen.sample ? 4 : 0) | 1;
-  int served = 1;
-  if (e->use_mega && e->cfg.tp_size == 1 && !e->gen.sample) {
-    served = run_mega(e, key, [&]() { return enqueue_round(e, E, d_req, 0); });
-    if (served < 0) return served;
-  }
-  if (served == 1) TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
+  TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
   (void)seq;
   TRY(peer_check(e));
   copy_result(e, out);
@@ -1323,12 +1235,7 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
   if (e->host_len + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
   const int nl = (e->gen.exit_layer > 0 && e->gen.exit_layer <= e->cfg.n_layers) ? e->gen.exit_layer : e->cfg.n_layers;
   const long long key = ((long long)nl << 20) | (e->gen.sample ? 4 : 0) | 2;
-  int served = 1;
-  if (e->use_mega && e->cfg.tp_size == 1 && !e->gen.sample) {
-    served = run_mega(e, key, [&]() { return enqueue_ar(e, nl, 0); });
-    if (served < 0) return served;
-  }
-  if (served == 1) TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
+  TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
   TRY(peer_check(e));
   *token_out = e->res_host->emitted_ids[0];
   e->host_len = e->res_host->kv_len;
@@ -1365,6 +1272,35 @@ int lsk_profile_round(lsk_engine* e, int32_t d_req, lsk_round_out* out, float* c
   e->prof_events.clear();
   copy_result(e, out);
   e->host_len = out->kv_len;
+  return LSK_OK;
+}
+
+// Teacher-forced block (parity tests): the m given token ids as rows 0..m-1 at positions
+// len .. len+m-1 through ALL layers and the LM head (logits kept: needs LSK_FLAG_KEEP_LOGITS).
+// Nothing is committed: the rows' K/V entries land beyond the committed length and are
+// overwritten by the next real step.  This is forward() of llama_model_utils.py:155-209 on a
+// block of m tokens on top of the committed context.
+int lsk_debug_forward_rows(lsk_engine* e, const int32_t* ids, int32_t m) {
+  if (!e || !ids) return fail(LSK_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_debug_forward_rows");
+  if (!e->keep_logits) return fail(LSK_ERR_STATE, "engine created without LSK_FLAG_KEEP_LOGITS");
+  if (m < 1 || m > e->max_rows) return fail(LSK_ERR_INVALID, "m %d out of [1,%d]", m, e->max_rows);
+  if (e->host_len + m + 1 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
+  const lsk_config& c = e->cfg;
+  for (int i = 0; i < m; ++i)
+    if (ids[i] < 0 || ids[i] >= c.vocab) return fail(LSK_ERR_INVALID, "token id %d out of range", ids[i]);
+  CU(cudaMemcpyAsync(e->d_prompt, ids, (size_t)m * 4, cudaMemcpyHostToDevice, e->stream));
+  e->cur_class = CLS_MISC;
+  CU(launch(e, embed_tokens_kernel, dim3(m), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+            (const int*)e->d_prompt, e->hidden, c.hidden));
+  for (int l = 0; l < c.n_layers; ++l) TRY(enqueue_layer(e, l, 0, m, &e->state->len, 0));
+  const int keep_sample = e->gen.sample;
+  e->gen.sample = 0;
+  const int st = enqueue_lm_head(e, 0, m);
+  e->gen.sample = keep_sample;
+  if (st != LSK_OK) return st;
+  CU(cudaStreamSynchronize(e->stream));
+  TRY(peer_check(e));
   return LSK_OK;
 }
 
@@ -1408,16 +1344,20 @@ int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index, fl
     return LSK_OK;
   }
   if (what == LSK_DBG_KROW || what == LSK_DBG_VROW) {
-    if (layer < 0 || layer >= e->cfg.n_layers || n != kHeadDim) return fail(LSK_ERR_INVALID, "bad layer / n");
+    const int hd = e->cfg.head_dim;
+    if (layer < 0 || layer >= e->cfg.n_layers || n != hd) return fail(LSK_ERR_INVALID, "bad layer / n (one row = head_dim floats)");
     const int64_t head = index / e->cfg.max_ctx, pos = index % e->cfg.max_ctx;
     if (head >= e->kv_heads_l) return fail(LSK_ERR_INVALID, "bad kv head");
     std::vector<int> pt(e->n_pages);
     CU(cudaMemcpy(pt.data(), e->page_table, pt.size() * 4, cudaMemcpyDeviceToHost));
     const __nv_bfloat16* pool = (what == LSK_DBG_KROW ? e->kpool : e->vpool) + (size_t)layer * e->pool_layer_elems;
-    const __nv_bfloat16* src = pool + ((size_t)(pt[pos >> 6] * e->kv_heads_l + head) * kPageTokens + (pos & 63)) * kHeadDim;
-    std::vector<__nv_bfloat16> tmp(kHeadDim);
-    CU(cudaMemcpy(tmp.data(), src, kHeadDim * 2, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < kHeadDim; ++i) dst[i] = __bfloat162float(tmp[i]);
+    // one token row is contiguous; its 16-byte chunks are swizzled (common.cuh: kv_elem_offset)
+    const __nv_bfloat16* src = pool + kv_elem_offset(hd, pt[pos >> 6], e->kv_heads_l, (int)head, (int)(pos & 63), 0) -
+                               (size_t)(kv_chunk_swizzle(hd, (int)(pos & 63)) * 8);
+    std::vector<__nv_bfloat16> tmp(hd);
+    CU(cudaMemcpy(tmp.data(), src, (size_t)hd * 2, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < hd; ++i)
+      dst[i] = __bfloat162float(tmp[(((i >> 3) ^ kv_chunk_swizzle(hd, (int)(pos & 63))) << 3) + (i & 7)]);
     return LSK_OK;
   }
   return fail(LSK_ERR_INVALID, "unknown debug selector %d", what);
@@ -1485,7 +1425,7 @@ int lsk_test_pack(const void* w, int64_t n, int64_t k, void* packed) {
   const int64_t pairs = n * (k / 2);
   int blocks = (int)((pairs + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_rows_kernel<<<blocks, 256>>>((const __nv_bfloat16*)w, k, 0, 0, n, k, (__nv_bfloat16*)packed, 0, MAP_PLAIN);
+  pack_rows_kernel<<<blocks, 256>>>((const __nv_bfloat16*)w, k, 0, 0, n, k, (__nv_bfloat16*)packed, 0, MAP_PLAIN, k, 128);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
   return LSK_OK;
@@ -1526,6 +1466,87 @@ int lsk_test_gemm(const void* packed, int64_t n, int64_t k, const void* x, int32
   }
   CU(cudaEventDestroy(e0));
   CU(cudaEventDestroy(e1));
+  CU(cudaStreamDestroy(tmp.stream));
+  tmp.stream = nullptr;
+  return LSK_OK;
+}
+
+// natural K/V [kv_head][ctx][hd] -> the engine's paged pool layout (one layer)
+__global__ void paginate_kv_kernel(const __nv_bfloat16* __restrict__ src, int n_kv, int ctx, int kHeadDim,
+                                   const int* __restrict__ page_table, __nv_bfloat16* __restrict__ pool) {
+  const int64_t total = (int64_t)n_kv * ctx * (kHeadDim / 8);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % (kHeadDim / 8));
+    const int pos = (int)((i / (kHeadDim / 8)) % ctx);
+    const int h = (int)(i / ((int64_t)(kHeadDim / 8) * ctx));
+    const uint4 v = *reinterpret_cast<const uint4*>(src + ((size_t)h * ctx + pos) * kHeadDim + ch * 8);
+    const int page = page_table[pos >> 6];
+    *reinterpret_cast<uint4*>(pool + kv_elem_offset(kHeadDim, page, n_kv, h, pos & 63, ch * 8)) = v;
+  }
+}
+
+// Stand-alone attention (unit test / micro-benchmark): m query rows at positions ctx-m .. ctx-1
+// attend causally to keys 0 .. ctx-1.  q / out: [m][n_heads * 128] bf16; k / v: natural
+// [n_kv_heads][ctx][128] bf16 (k already rotated); page_perm (host, may be null) permutes the
+// logical -> physical page map.  Same launch path as the engine (cluster kernel).
+int lsk_test_attn(const void* q, const void* k, const void* v, int32_t n_heads, int32_t n_kv_heads,
+                  int32_t head_dim, int32_t ctx, int32_t m, int32_t n_splits, const int32_t* page_perm, void* out,
+                  int32_t iters, float* avg_ms) {
+  const int kHeadDim = head_dim;
+  if (head_dim != 32 && head_dim != 64 && head_dim != 128) return fail(LSK_ERR_INVALID, "head_dim %d unsupported", head_dim);
+  if (!q || !k || !v || !out || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads || ctx < m || m < 1 ||
+      m > kMaxRows || n_splits < 1 || n_splits > 8)
+    return fail(LSK_ERR_INVALID, "bad attention test shape");
+  lsk_engine tmp;
+  CU(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
+  tmp.use_pdl = true;
+  const int n_pages = (ctx + kPageTokens - 1) / kPageTokens;
+  const size_t pool_elems = (size_t)n_pages * n_kv_heads * kPageTokens * kHeadDim;
+  __nv_bfloat16 *kp = nullptr, *vp = nullptr;
+  int *pt = nullptr, *len = nullptr;
+  CU(cudaMalloc((void**)&kp, pool_elems * 2));
+  CU(cudaMalloc((void**)&vp, pool_elems * 2));
+  CU(cudaMalloc((void**)&pt, (size_t)n_pages * 4));
+  CU(cudaMalloc((void**)&len, 4));
+  CU(cudaMemsetAsync(kp, 0, pool_elems * 2, tmp.stream));
+  CU(cudaMemsetAsync(vp, 0, pool_elems * 2, tmp.stream));
+  std::vector<int> pth(n_pages);
+  for (int i = 0; i < n_pages; ++i) pth[i] = page_perm ? page_perm[i] : i;
+  for (int i = 0; i < n_pages; ++i)
+    if (pth[i] < 0 || pth[i] >= n_pages) return fail(LSK_ERR_INVALID, "bad page permutation");
+  const int base = ctx - m;
+  CU(cudaMemcpyAsync(pt, pth.data(), (size_t)n_pages * 4, cudaMemcpyHostToDevice, tmp.stream));
+  CU(cudaMemcpyAsync(len, &base, 4, cudaMemcpyHostToDevice, tmp.stream));
+  paginate_kv_kernel<<<148 * 4, 256, 0, tmp.stream>>>((const __nv_bfloat16*)k, n_kv_heads, ctx, head_dim, pt, kp);
+  paginate_kv_kernel<<<148 * 4, 256, 0, tmp.stream>>>((const __nv_bfloat16*)v, n_kv_heads, ctx, head_dim, pt, vp);
+  CU(cudaGetLastError());
+  AttnArgs a{};
+  a.q = (const __nv_bfloat16*)q; a.q_ld = n_heads * kHeadDim;
+  a.out = (__nv_bfloat16*)out; a.out_ld = n_heads * kHeadDim;
+  a.kpool = kp; a.vpool = vp; a.page_table = pt; a.base_len = len; a.pos_off = 0; a.M = m;
+  a.group = n_heads / n_kv_heads; a.n_kv_heads = n_kv_heads; a.n_splits = n_splits;
+  a.scale = 1.0f / sqrtf((float)kHeadDim);
+  int st = launch_attention(&tmp, a, head_dim);
+  if (st != LSK_OK) return st;
+  CU(cudaStreamSynchronize(tmp.stream));
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, tmp.stream));
+    for (int i = 0; i < iters; ++i) {
+      st = launch_attention(&tmp, a, head_dim);
+      if (st != LSK_OK) return st;
+    }
+    CU(cudaEventRecord(e1, tmp.stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = ms / iters;
+    CU(cudaEventDestroy(e0));
+    CU(cudaEventDestroy(e1));
+  }
+  cudaFree(kp); cudaFree(vp); cudaFree(pt); cudaFree(len);
   CU(cudaStreamDestroy(tmp.stream));
   tmp.stream = nullptr;
   return LSK_OK;

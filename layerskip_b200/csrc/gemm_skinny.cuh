@@ -58,37 +58,6 @@ __device__ __forceinline__ void bar_arrive(int id, int n) {
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-// ---- mbarrier + TMA bulk copy
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 struct GemmArgs {
   const uint4* W;       // packed weights
   int n_tiles;          // N / 16
@@ -125,8 +94,9 @@ struct GemmArgs {
   const int* page_table;
   const int* base_len;
   int pos_off;
-  const float2* rope;    // [max_pos][64] (cos, sin)
-  int q_rows;            // local q rows (heads * 128)
+  const float2* rope;    // [max_pos][head_dim / 2] (cos, sin)
+  int head_dim;
+  int q_rows;            // local q rows (heads * head_dim)
   int kv_rows;           // local kv rows
   int n_kv_heads;        // local
   // ---- LMHEAD
@@ -425,14 +395,14 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
   for (int i = 0; i < kRowsPerEwarp; ++i) { best_v[i] = -INFINITY; best_i[i] = 0x7fffffff; }
 
   // EPI_PUSH: where this rank's slot lives inside every rank's region for the current instance
+  // (LL lines, tp_peer.cuh: {v0, epoch, v1, epoch} — the flag travels inside the data)
   unsigned int push_epoch = 0;
-  size_t push_off = 0, push_ar = 0, push_flags = 0;
+  size_t push_line0 = 0, push_ll = 0;
   if (EPI == EPI_PUSH) {
     const PeerRegionLayout PL = peer_region_layout(pc->size, pc->hidden);
     push_epoch = *reinterpret_cast<volatile unsigned int*>(peer_base(*pc, pc->rank) + PL.local) + 1u;
-    push_off = ((size_t)(push_epoch & 1u) * pc->size + pc->rank) * kMaxRows * pc->hidden;   // floats
-    push_ar = PL.ar_data;
-    push_flags = PL.gemm_flags;
+    push_line0 = ((size_t)(push_epoch & 1u) * pc->size + pc->rank) * ((size_t)kMaxRows * pc->hidden / 2);
+    push_ll = PL.ll_data;
   }
 
   int it = 0;
@@ -494,33 +464,30 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
         } else {
           const int pr = tile * 16;                     // first packed row of the tile
           const int pos = *a.base_len + a.pos_off + m;
-          if (pr < a.q_rows + a.kv_rows) {              // q or k: rotary pair (d, d + 64)
+          const int HD = a.head_dim, half = HD >> 1;
+          if (pr < a.q_rows + a.kv_rows) {              // q or k: rotary pair (d, d + HD/2)
             const bool is_q = pr < a.q_rows;
             const int rel = is_q ? pr : pr - a.q_rows;
-            const int head = rel >> 7, tt = (rel & 127) >> 4;
+            const int head = rel / HD, tt = (rel % HD) >> 4;
             const int d = tt * 8 + r;
-            const float2 cs = a.rope[(size_t)pos * 64 + d];
+            const float2 cs = a.rope[(size_t)pos * half + d];
             const float o_lo = lo * cs.x - hi * cs.y;
             const float o_hi = hi * cs.x + lo * cs.y;
             if (is_q) {
-              __nv_bfloat16* qd = a.q_out + (size_t)m * a.q_ld + head * 128;
+              __nv_bfloat16* qd = a.q_out + (size_t)m * a.q_ld + head * HD;
               qd[d] = __float2bfloat16_rn(o_lo);
-              qd[d + 64] = __float2bfloat16_rn(o_hi);
+              qd[d + half] = __float2bfloat16_rn(o_hi);
             } else {
               const int page = a.page_table[pos >> 6];
-              __nv_bfloat16* kd = a.kpool +
-                  ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
-              kd[d] = __float2bfloat16_rn(o_lo);
-              kd[d + 64] = __float2bfloat16_rn(o_hi);
+              a.kpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d)] = __float2bfloat16_rn(o_lo);
+              a.kpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d + half)] = __float2bfloat16_rn(o_hi);
             }
           } else {                                       // v: natural order, no rotation
             const int rel = pr - a.q_rows - a.kv_rows;
-            const int head = rel >> 7, d0 = rel & 127;
+            const int head = rel / HD, d0 = rel % HD;
             const int page = a.page_table[pos >> 6];
-            __nv_bfloat16* vd = a.vpool +
-                ((size_t)(page * a.n_kv_heads + head) * kPageTokens + (pos & 63)) * 128;
-            vd[d0 + r] = __float2bfloat16_rn(lo);
-            vd[d0 + r + 8] = __float2bfloat16_rn(hi);
+            a.vpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d0 + r)] = __float2bfloat16_rn(lo);
+            a.vpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d0 + r + 8)] = __float2bfloat16_rn(hi);
           }
         }
       }
@@ -541,11 +508,15 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
         } else if (EPI == EPI_STORE) {
           if (m < a.M) a.out_f32[(size_t)m * a.out_ld + orow] = v;
         } else if (EPI == EPI_PUSH) {
-          if (m < a.M) {
+          // rows (orow, orow + 1) of one token -> one 16-byte line to every rank (own included);
+          // `items` is a multiple of 32 and `tile` is warp-uniform, so the shuffle is convergent
+          const float vn = __shfl_down_sync(0xffffffffu, v, 1);
+          if (m < a.M && !(row & 1)) {
+            const size_t line = push_line0 + ((size_t)m * pc->hidden + orow) / 2;
 #pragma unroll
             for (int r = 0; r < kMaxPeers; ++r)
               if (r < pc->size)
-                reinterpret_cast<float*>(pc->base[r] + push_ar)[push_off + (size_t)m * pc->hidden + orow] = v;
+                ll_store(reinterpret_cast<uint4*>(pc->base[r] + push_ll) + line, v, vn, push_epoch);
           }
         } else {  // LMHEAD
           if (m < a.M && a.logits != nullptr && orow < a.n_valid_rows)
@@ -581,16 +552,6 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
       }
     }
     if (slot + 2 * gridDim.x < n_slots) bar_arrive(BAR_EMPTY0 + buf, kWorkThreads);
-  }
-
-  if (EPI == EPI_PUSH) {
-    // all of this CTA's tiles are on their way: make them visible system-wide, then tell every
-    // rank (this one included) that CTA blockIdx.x of rank pc->rank is done with this instance
-    __threadfence_system();
-    bar_sync(BAR_EPI, kEpiThreads);
-    if (etid < pc->size)
-      st_release_sys(reinterpret_cast<unsigned int*>(peer_base(*pc, etid) + push_flags) +
-                         pc->rank * kMaxGemmCtas + blockIdx.x, push_epoch);
   }
 
   if (EPI == EPI_LMHEAD) {

@@ -11,12 +11,13 @@ namespace lsk {
 // ---------------------------------------------------------------------------------------
 enum { MAP_PLAIN = 0, MAP_ROPE_HEADS = 1, MAP_GATE = 2, MAP_UP = 3 };
 
-__host__ __device__ inline int64_t map_row(int mode, int64_t r) {
+__host__ __device__ inline int64_t map_row(int mode, int64_t r, int hd = 128) {
   switch (mode) {
-    case MAP_ROPE_HEADS: {  // rotary pair (d, d+64) -> rows (r, r+8) of one 16-row tile
-      const int64_t head = r >> 7, d = r & 127;
-      const int64_t dd = d & 63, tt = dd >> 3;
-      return head * 128 + tt * 16 + (d >= 64 ? 8 : 0) + (dd & 7);
+    case MAP_ROPE_HEADS: {  // rotary pair (d, d + hd/2) -> rows (r, r+8) of one 16-row tile
+      const int64_t half = hd >> 1;
+      const int64_t head = r / hd, d = r % hd;
+      const int64_t dd = d % half, tt = dd >> 3;
+      return head * hd + tt * 16 + (d >= half ? 8 : 0) + (dd & 7);
     }
     case MAP_GATE: return (r >> 3) * 16 + (r & 7);
     case MAP_UP: return (r >> 3) * 16 + 8 + (r & 7);
@@ -32,17 +33,20 @@ __host__ __device__ inline int64_t packed_elem_offset(int64_t pr, int64_t k, int
   return ((((tile * nsb + sb) * 2 + j) * 32 + lane) * 4 + reg) * 2 + half;
 }
 
+// K = source columns taken (even); K_dst = padded K of the packed matrix (multiple of 32; columns
+// K .. K_dst-1 keep whatever dst holds: the engine zero-fills its weight buffers at allocation)
 __global__ void pack_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld,
                                  int64_t src_row0, int64_t src_col0, int64_t n_rows, int64_t K,
-                                 __nv_bfloat16* __restrict__ dst, int64_t dst_row0, int mode) {
-  const int64_t nsb = K >> 5;
+                                 __nv_bfloat16* __restrict__ dst, int64_t dst_row0, int mode,
+                                 int64_t K_dst, int hd) {
+  const int64_t nsb = K_dst >> 5;
   const int64_t pairs = n_rows * (K >> 1);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pairs;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (K >> 1), k = (i % (K >> 1)) * 2;
     const uint32_t v = *reinterpret_cast<const uint32_t*>(
         src + (src_row0 + r) * src_ld + src_col0 + k);
-    const int64_t pr = dst_row0 + map_row(mode, r);
+    const int64_t pr = dst_row0 + map_row(mode, r, hd);
     *reinterpret_cast<uint32_t*>(dst + packed_elem_offset(pr, k, nsb)) = v;
   }
 }

@@ -42,7 +42,8 @@ constexpr long long kPeerTimeoutCycles = 4000000000LL;  // ~2 s at 1.9 GHz
 
 // Byte offsets inside one rank's peer-visible region.
 struct PeerRegionLayout {
-  size_t ar_data;    // float  [2 parities][tp][kMaxRows * hidden]
+  size_t ar_data;    // float  [2 parities][tp][kMaxRows * hidden]   (fence + flag protocol)
+  size_t ll_data;    // LL lines [2 parities][tp][kMaxRows * hidden / 2] x 16 B: {v0, flag, v1, flag}
   size_t ar_flags;   // uint32 [tp][kMaxArCtas]
   size_t g_data;     // uint32 [2 parities][tp][32]   (16 fp32 values + 16 int32 indices)
   size_t g_flags;    // uint32 [tp]
@@ -55,6 +56,7 @@ __host__ __device__ inline PeerRegionLayout peer_region_layout(int tp, int hidde
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
   L.ar_data = take((size_t)2 * tp * kMaxRows * hidden * 4);
+  L.ll_data = take((size_t)2 * tp * kMaxRows * hidden * 8);
   L.ar_flags = take((size_t)tp * kMaxArCtas * 4);
   L.g_data = take((size_t)2 * tp * 32 * 4);
   L.g_flags = take((size_t)tp * 4);
@@ -163,45 +165,39 @@ tp_allreduce_resid_kernel(const PeerComm pc, const float* __restrict__ partial,
   }
 }
 
-// FUSED mode (LSK_TP_ONESHOT=2): the row-parallel GEMM's epilogue (gemm_skinny.cuh, EPI_PUSH) has
-// already written its output tiles into slot [parity][my rank] of EVERY rank's region (its own
-// included) while the kernel was still streaming weights, and each of its CTAs raised
-// gemm_flags[my rank][cta].  This kernel only waits for the n_src CTAs of every rank, adds the
-// partials in rank order and the residual, and advances the epoch.
-__global__ void __launch_bounds__(kArThreads)
-tp_finish_resid_kernel(const PeerComm pc, float* __restrict__ x, int n4, int n_src) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const PeerRegionLayout L = peer_region_layout(pc.size, pc.hidden);
-  unsigned char* mine = peer_base(pc, pc.rank);
-  volatile unsigned int* epoch_p = reinterpret_cast<volatile unsigned int*>(mine + L.local);
-  int* ticket_p = reinterpret_cast<int*>(mine + L.local + 4);
-  const unsigned int epoch = *epoch_p + 1u;
-  const size_t slot4 = (size_t)kMaxRows * pc.hidden / 4;
-  const size_t par4 = (size_t)(epoch & 1u) * pc.size * slot4;
-  const int tid = threadIdx.x, c = blockIdx.x;
-  const unsigned int* flags = reinterpret_cast<const unsigned int*>(mine + L.gemm_flags);
-  for (int k = tid; k < pc.size * n_src; k += kArThreads) {
-    const int r = k / n_src, cta = k - r * n_src;
-    if (!peer_wait(flags + r * kMaxGemmCtas + cta, epoch)) *reinterpret_cast<volatile int*>(pc.error) = 1;
+// ---------------------------------------------------------------------------------------------
+// LL ("low latency") variants: the flag travels INSIDE the data.  A 16-byte line carries two fp32
+// values and the instance's epoch twice — {v0, epoch, v1, epoch} — and 8-byte aligned halves are
+// single-copy atomic, so a reader that sees the epoch in both halves has the values: no
+// __threadfence_system(), no separate flag store, no second NVLink round trip.  The element a
+// thread pushes is the element it reduces, so the kernel needs no intra-CTA synchronisation
+// either.  Cost: 2x the bytes on NVLink (229 KiB per peer for a 7 x 4096 block: ~0.5 us).
+// Same hazards argument as above (epoch in device memory, two parities, monotone instances).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4* p, float v0, float v1, unsigned int flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)),
+               "r"(flag), "r"(__float_as_uint(v1)), "r"(flag) : "memory");
+}
+// spin until both halves of the line carry `flag`; false on timeout
+__device__ __forceinline__ bool ll_load(const uint4* p, unsigned int flag, float& v0, float& v1) {
+  const long long t0 = clock64();
+  uint4 q;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+    if (q.y == flag && q.w == flag) break;
+    if (clock64() - t0 > kPeerTimeoutCycles) { v0 = v1 = 0.f; return false; }
   }
+  v0 = __uint_as_float(q.x);
+  v1 = __uint_as_float(q.z);
+  return true;
+}
+
+// last CTA to finish advances the epoch (every CTA read it at its start)
+__device__ __forceinline__ void peer_advance_epoch(volatile unsigned int* epoch_p, int* ticket_p,
+                                                   unsigned int epoch) {
   __syncthreads();
-  const int i0 = c * kArVecPerCta;
-  const int i1 = (i0 + kArVecPerCta < n4) ? i0 + kArVecPerCta : n4;
-  const float4* recv = reinterpret_cast<const float4*>(mine + L.ar_data) + par4;
-  float4* x4 = reinterpret_cast<float4*>(x);
-  for (int i = i0 + tid; i < i1; i += kArThreads) {
-    float4 acc = __ldcg(recv + i);
-    for (int r = 1; r < pc.size; ++r) {
-      const float4 v = __ldcg(recv + (size_t)r * slot4 + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    float4 h = x4[i];
-    h.x += acc.x; h.y += acc.y; h.z += acc.z; h.w += acc.w;
-    x4[i] = h;
-  }
-  __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     __threadfence();
     const int t = atomicAdd(ticket_p, 1);
     if (t == (int)gridDim.x - 1) {
@@ -210,6 +206,77 @@ tp_finish_resid_kernel(const PeerComm pc, float* __restrict__ x, int n4, int n_s
       __threadfence();
     }
   }
+}
+
+// x[0 .. 2*n2) += sum over ranks (rank order) of partial_r.  One launch = push + reduce.
+__global__ void __launch_bounds__(kArThreads)
+tp_allreduce_ll_kernel(const PeerComm pc, const float* __restrict__ partial, float* __restrict__ x, int n2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const PeerRegionLayout L = peer_region_layout(pc.size, pc.hidden);
+  unsigned char* mine = peer_base(pc, pc.rank);
+  volatile unsigned int* epoch_p = reinterpret_cast<volatile unsigned int*>(mine + L.local);
+  int* ticket_p = reinterpret_cast<int*>(mine + L.local + 4);
+  const unsigned int epoch = *epoch_p + 1u;
+  const size_t slot = (size_t)kMaxRows * pc.hidden / 2;             // lines per (parity, rank)
+  const size_t par = (size_t)(epoch & 1u) * pc.size * slot;
+  const float2* p2 = reinterpret_cast<const float2*>(partial);
+  float2* x2 = reinterpret_cast<float2*>(x);
+  const uint4* recv = reinterpret_cast<const uint4*>(mine + L.ll_data) + par;
+  bool ok = true;
+  for (int i = blockIdx.x * kArThreads + threadIdx.x; i < n2; i += gridDim.x * kArThreads) {
+    const float2 own = __ldcg(p2 + i);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (r >= pc.size || r == pc.rank) continue;
+      ll_store(reinterpret_cast<uint4*>(pc.base[r] + L.ll_data) + par + (size_t)pc.rank * slot + i, own.x, own.y, epoch);
+    }
+    float2 h = x2[i];                                              // overlaps the NVLink flight
+    float2 acc = make_float2(0.f, 0.f);
+    for (int r = 0; r < pc.size; ++r) {
+      float v0 = own.x, v1 = own.y;
+      if (r != pc.rank) ok &= ll_load(recv + (size_t)r * slot + i, epoch, v0, v1);
+      if (r == 0) acc = make_float2(v0, v1);
+      else { acc.x += v0; acc.y += v1; }
+    }
+    h.x += acc.x; h.y += acc.y;
+    x2[i] = h;
+  }
+  if (!ok) *reinterpret_cast<volatile int*>(pc.error) = 1;
+  peer_advance_epoch(epoch_p, ticket_p, epoch);
+}
+
+// Fused mode: the row-parallel GEMM's epilogue (gemm_skinny.cuh, EPI_PUSH) wrote LL lines of its
+// output tiles into slot [parity][its rank] of EVERY rank's region (its own included) while it
+// was still streaming weights.  This kernel only polls the lines, sums in rank order and adds the
+// residual — the NVLink transfer overlapped the GEMM tile by tile.
+__global__ void __launch_bounds__(kArThreads)
+tp_finish_ll_kernel(const PeerComm pc, float* __restrict__ x, int n2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const PeerRegionLayout L = peer_region_layout(pc.size, pc.hidden);
+  unsigned char* mine = peer_base(pc, pc.rank);
+  volatile unsigned int* epoch_p = reinterpret_cast<volatile unsigned int*>(mine + L.local);
+  int* ticket_p = reinterpret_cast<int*>(mine + L.local + 4);
+  const unsigned int epoch = *epoch_p + 1u;
+  const size_t slot = (size_t)kMaxRows * pc.hidden / 2;
+  const uint4* recv = reinterpret_cast<const uint4*>(mine + L.ll_data) + (size_t)(epoch & 1u) * pc.size * slot;
+  float2* x2 = reinterpret_cast<float2*>(x);
+  bool ok = true;
+  for (int i = blockIdx.x * kArThreads + threadIdx.x; i < n2; i += gridDim.x * kArThreads) {
+    float2 h = x2[i];
+    float2 acc = make_float2(0.f, 0.f);
+    for (int r = 0; r < pc.size; ++r) {
+      float v0, v1;
+      ok &= ll_load(recv + (size_t)r * slot + i, epoch, v0, v1);
+      if (r == 0) acc = make_float2(v0, v1);
+      else { acc.x += v0; acc.y += v1; }
+    }
+    h.x += acc.x; h.y += acc.y;
+    x2[i] = h;
+  }
+  if (!ok) *reinterpret_cast<volatile int*>(pc.error) = 1;
+  peer_advance_epoch(epoch_p, ticket_p, epoch);
 }
 
 // Vocab-parallel LM head: this rank's best (value, index) per row from its arg-max candidates,

@@ -14,7 +14,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .weights import LlamaArch, SyntheticLlama, iter_state_dict
+from .weights import ROPE_KINDS, LlamaArch, SyntheticLlama, iter_state_dict
 
 
 @dataclass
@@ -32,7 +32,7 @@ class Engine:
     def __init__(self, arch: LlamaArch, max_ctx: int = 4096, tp_rank: int = 0, tp_size: int = 1,
                  keep_logits: bool = False, use_pdl: bool = True, use_graph: bool = True,
                  attn_splits: int = 0, device: Optional[torch.device] = None,
-                 use_megakernel: bool = False, tp_oneshot: bool = False):
+                 tp_nccl: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("layerskip_b200 needs a CUDA device (B200); there is no CPU path")
         self._lib = _lib.load()
@@ -42,13 +42,16 @@ class Engine:
         self.tp_rank, self.tp_size = tp_rank, tp_size
         flags = (_lib.LSK_FLAG_KEEP_LOGITS if keep_logits else 0) | \
                 (0 if use_pdl else _lib.LSK_FLAG_NO_PDL) | (0 if use_graph else _lib.LSK_FLAG_NO_GRAPH) | \
-                (_lib.LSK_FLAG_MEGAKERNEL if use_megakernel else 0) | \
-                (_lib.LSK_FLAG_TP_ONESHOT if tp_oneshot else 0)
+                (_lib.LSK_FLAG_TP_NCCL if tp_nccl else 0)
         cfg = _lib.lsk_config(
             vocab=arch.vocab, hidden=arch.hidden, inter=arch.inter, n_layers=arch.layers,
             n_heads=arch.heads, n_kv_heads=arch.kv_heads, head_dim=arch.head_dim,
             rms_eps=arch.rms_eps, rope_theta=arch.rope_theta, max_ctx=max_ctx, tp_rank=tp_rank,
-            tp_size=tp_size, attn_splits=attn_splits, flags=flags)
+            tp_size=tp_size, attn_splits=attn_splits, flags=flags,
+            rope_scaling=ROPE_KINDS[arch.rope_scaling], rope_factor=arch.rope_factor,
+            rope_low_freq_factor=arch.rope_low_freq_factor,
+            rope_high_freq_factor=arch.rope_high_freq_factor,
+            rope_original_max_pos=arch.rope_original_max_pos)
         self.max_ctx = max_ctx
         self.keep_logits = keep_logits
         # refuse a configuration that cannot fit BEFORE cudaMalloc fails half-way (memory.py)
@@ -206,6 +209,15 @@ class Engine:
         _lib.check(self._lib.lsk_ar_bytes(self._h, ctx, C.byref(v)))
         return v.value
 
+    def debug_forward_rows(self, ids: Sequence[int]) -> torch.Tensor:
+        """Teacher-forced block (parity tests): logits [len(ids), vocab_local] of the given ids
+        run as ONE block on top of the committed context; nothing is committed."""
+        m = len(ids)
+        arr = (C.c_int32 * m)(*[int(t) for t in ids])
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_forward_rows(self._h, arr, m))
+        return self.debug_logits(m)
+
     def debug_hidden(self, rows: int = 16) -> torch.Tensor:
         n = rows * self.arch.hidden
         buf = (C.c_float * n)()
@@ -232,11 +244,12 @@ class Engine:
         return torch.frombuffer(buf, dtype=torch.float32).clone().view(rows, self.arch.vocab)
 
     def debug_kv_row(self, which: str, layer: int, kv_head: int, pos: int) -> torch.Tensor:
-        buf = (C.c_float * 128)()
+        hd = self.arch.head_dim
+        buf = (C.c_float * hd)()
         what = _lib.LSK_DBG_KROW if which == "k" else _lib.LSK_DBG_VROW
         with torch.cuda.device(self.device):
             _lib.check(self._lib.lsk_debug_read(self._h, what, layer, kv_head * self.max_ctx + pos,
-                                                buf, 128))
+                                                buf, hd))
         return torch.tensor(list(buf), dtype=torch.float32)
 
     def debug_set_page_table(self, pages: Sequence[int]) -> None:

@@ -24,9 +24,10 @@ def plan_memory(arch: LlamaArch, max_ctx: int = 4096, tp_size: int = 1, sampling
     q_l = arch.heads // tp_size * arch.head_dim
     kv_l = arch.kv_heads // tp_size * arch.head_dim
     inter_l = arch.inter // tp_size
+    inter_l_pad = (inter_l + 31) // 32 * 32                 # K of the down projection
     vocab_l = arch.vocab // tp_size
     vocab_l_pad = (vocab_l + 15) // 16 * 16
-    per_layer = 2 * ((q_l + 2 * kv_l) * h + h * q_l + 2 * inter_l * h + h * inter_l) + 2 * 2 * h
+    per_layer = 2 * ((q_l + 2 * kv_l) * h + h * q_l + 2 * inter_l * h + h * inter_l_pad) + 2 * 2 * h
     weights = L * per_layer
     embed = 2 * arch.vocab * h + 2 * h                       # replicated embedding + final norm
     lm_head = 2 * vocab_l_pad * h
@@ -35,14 +36,12 @@ def plan_memory(arch: LlamaArch, max_ctx: int = 4096, tp_size: int = 1, sampling
     n_pages = (max_ctx + PAGE_TOKENS - 1) // PAGE_TOKENS
     max_pos = n_pages * PAGE_TOKENS
     kv_pool = 2 * L * n_pages * (arch.kv_heads // tp_size) * PAGE_TOKENS * arch.head_dim * 2
-    group = arch.heads // arch.kv_heads
     scratch = (
         (MAX_ROWS + 1) * h * 4                 # residual rows
         + 2 * MAX_ROWS * q_l * 2               # q, attention out
-        + MAX_ROWS * inter_l * 2               # SiLU * up
+        + MAX_ROWS * inter_l_pad * 2           # SiLU * up
         + MAX_ROWS * h * 4                     # TP partial sums
-        + max_pos * 64 * 8 + max_pos * 4 + n_pages * 4      # RoPE table, prompt ids, page table
-        + (arch.kv_heads // tp_size) * 8 * group * 16 * (arch.head_dim + 2) * 4   # split-KV partials
+        + max_pos * (arch.head_dim // 2) * 8 + max_pos * 4 + n_pages * 4   # RoPE table, prompt ids, page table
         + 148 * MAX_ROWS * 8 + tp_size * MAX_ROWS * 8)      # arg-max candidates
     if keep_logits or sampling:
         scratch += MAX_ROWS * vocab_l_pad * 4

@@ -27,6 +27,39 @@ _GLOBAL_ROLES = {"model.embed_tokens.weight": _lib.LSK_W_EMBED,
                  "lm_head.weight": _lib.LSK_W_LM_HEAD}
 
 
+ROPE_KINDS = {"default": _lib.LSK_ROPE_DEFAULT, "linear": _lib.LSK_ROPE_LINEAR,
+              "llama3": _lib.LSK_ROPE_LLAMA3}
+
+
+def parse_rope(cfg_get) -> Dict[str, float]:
+    """RoPE settings from an HF config, whichever spelling it uses: transformers 4.x keeps
+    `rope_theta` + `rope_scaling` (keys `rope_type` or the older `type`), transformers 5.x one
+    `rope_parameters` dict.  `cfg_get(name)` returns the attribute / key or None.  Unsupported
+    rule -> NotImplementedError (an unscaled table would give silently wrong logits)."""
+    theta = cfg_get("rope_theta")
+    out = dict(rope_scaling="default", rope_factor=1.0, rope_low_freq_factor=1.0,
+               rope_high_freq_factor=4.0, rope_original_max_pos=8192)
+    for key in ("rope_parameters", "rope_scaling"):
+        rp = cfg_get(key)
+        if not isinstance(rp, dict):
+            continue
+        if rp.get("rope_theta") is not None:
+            theta = rp["rope_theta"]
+        kind = rp.get("rope_type", rp.get("type", "default")) or "default"
+        if kind == "default":
+            continue
+        if kind not in ROPE_KINDS:
+            raise NotImplementedError(f"rope scaling {kind!r} is not supported (default, linear, llama3)")
+        out["rope_scaling"] = kind
+        out["rope_factor"] = float(rp["factor"])
+        if kind == "llama3":
+            out["rope_low_freq_factor"] = float(rp["low_freq_factor"])
+            out["rope_high_freq_factor"] = float(rp["high_freq_factor"])
+            out["rope_original_max_pos"] = int(rp["original_max_position_embeddings"])
+    out["rope_theta"] = float(theta if theta is not None else 10000.0)
+    return out
+
+
 @dataclass(frozen=True)
 class LlamaArch:
     """Architecture numbers the engine needs (what the reference reads from `model.config`)."""
@@ -39,23 +72,31 @@ class LlamaArch:
     head_dim: int = 128
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
+    rope_scaling: str = "default"          # default | linear | llama3 (HF modeling_rope_utils.py)
+    rope_factor: float = 1.0
+    rope_low_freq_factor: float = 1.0
+    rope_high_freq_factor: float = 4.0
+    rope_original_max_pos: int = 8192
 
     @staticmethod
     def from_hf_config(cfg) -> "LlamaArch":
         head_dim = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
-        theta = None
-        rp = getattr(cfg, "rope_parameters", None)
-        if isinstance(rp, dict):
-            theta = rp.get("rope_theta")
-            if rp.get("rope_type", "default") not in ("default", None):
-                raise NotImplementedError(f"rope_type {rp.get('rope_type')!r} is not supported")
-        if theta is None:
-            theta = getattr(cfg, "rope_theta", 10000.0)
+        rope = parse_rope(lambda name: getattr(cfg, name, None))
         return LlamaArch(vocab=cfg.vocab_size, hidden=cfg.hidden_size,
                          inter=cfg.intermediate_size, layers=cfg.num_hidden_layers,
                          heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads,
-                         head_dim=head_dim, rms_eps=float(cfg.rms_norm_eps),
-                         rope_theta=float(theta))
+                         head_dim=head_dim, rms_eps=float(cfg.rms_norm_eps), **rope)
+
+    def rope_config(self) -> Dict:
+        """HF-style `rope_scaling` dict (None for the default rule)."""
+        if self.rope_scaling == "default":
+            return None
+        d = {"rope_type": self.rope_scaling, "factor": self.rope_factor}
+        if self.rope_scaling == "llama3":
+            d.update(low_freq_factor=self.rope_low_freq_factor,
+                     high_freq_factor=self.rope_high_freq_factor,
+                     original_max_position_embeddings=self.rope_original_max_pos)
+        return d
 
     @property
     def q_dim(self) -> int:
@@ -81,6 +122,11 @@ ARCHS: Dict[str, LlamaArch] = {
     "tiny-mha": LlamaArch(512, 256, 704, 4, 2, 2, 128, 1e-5, 10000.0),
     "tiny-gqa": LlamaArch(640, 512, 1408, 6, 4, 2, 128, 1e-5, 10000.0),
     "small-1b": LlamaArch(32000, 2048, 5632, 8, 16, 16, 128, 1e-5, 10000.0),
+    # facebook/layerskip-llama3.2-1B shape (the reference's own test model, tests/tests_constants.py:9):
+    # head_dim 64, grouped KV, llama3 RoPE scaling, tied embeddings
+    "llama3.2-1b": LlamaArch(128256, 2048, 8192, 16, 32, 8, 64, 1e-5, 500000.0, "llama3", 32.0, 1.0, 4.0, 8192),
+    # correctness.py's CPU-runnable config (BASELINE.json configs[0])
+    "survey-tiny": LlamaArch(512, 256, 688, 4, 8, 8, 32, 1e-5, 10000.0),
 }
 
 
@@ -137,7 +183,7 @@ class SyntheticLlama:
             vocab_size=a.vocab, hidden_size=a.hidden, intermediate_size=a.inter,
             num_hidden_layers=a.layers, num_attention_heads=a.heads,
             num_key_value_heads=a.kv_heads, head_dim=a.head_dim, rms_norm_eps=a.rms_eps,
-            rope_theta=a.rope_theta))()
+            rope_theta=a.rope_theta, rope_scaling=a.rope_config()))()
 
     def names(self):
         a = self.arch

@@ -47,6 +47,8 @@ class LlamaDims:
     head_dim: int
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
+    # HF `rope_scaling` dict (rope_type "linear" | "llama3" + its parameters) or None
+    rope_scaling: Optional[Dict] = None
 
     @property
     def q_dim(self) -> int:
@@ -83,11 +85,15 @@ def dims_from_hf_config(cfg) -> LlamaDims:
         theta = rp.get("rope_theta")
     if theta is None:
         theta = getattr(cfg, "rope_theta", 10000.0)
+    scaling = None
+    for src in (rp, getattr(cfg, "rope_scaling", None)):
+        if isinstance(src, dict) and src.get("rope_type", src.get("type", "default")) not in (None, "default"):
+            scaling = {k: v for k, v in src.items() if k != "rope_theta"}
     return LlamaDims(
         vocab=cfg.vocab_size, hidden=cfg.hidden_size, inter=cfg.intermediate_size,
         layers=cfg.num_hidden_layers, heads=cfg.num_attention_heads,
         kv_heads=cfg.num_key_value_heads, head_dim=head_dim,
-        rms_eps=float(cfg.rms_norm_eps), rope_theta=float(theta))
+        rms_eps=float(cfg.rms_norm_eps), rope_theta=float(theta), rope_scaling=scaling)
 
 
 def weights_from_state_dict(dims: LlamaDims, sd: Dict[str, torch.Tensor],
@@ -128,10 +134,34 @@ def rope_tables(dims: LlamaDims, positions: torch.Tensor, dtype: torch.dtype
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """modeling_llama.py:73-135 — inv_freq = theta^(-2i/d); angle table duplicated over halves."""
     half = torch.arange(0, dims.head_dim, 2, dtype=torch.int64).to(torch.float32)
-    inv_freq = 1.0 / (dims.rope_theta ** (half / dims.head_dim))
+    inv_freq = scale_inv_freq(1.0 / (dims.rope_theta ** (half / dims.head_dim)), dims.rope_scaling)
     ang = positions.to(torch.float32)[:, None] * inv_freq[None, :]          # [s, d/2]
     ang = torch.cat([ang, ang], dim=-1)                                      # [s, d]
     return ang.cos().to(dtype), ang.sin().to(dtype)
+
+
+def scale_inv_freq(inv_freq: torch.Tensor, rs: Optional[Dict]) -> torch.Tensor:
+    """transformers modeling_rope_utils.py, restated: `_compute_linear_scaling_rope_parameters`
+    (inv_freq / factor) and `_compute_llama3_parameters` (wavelengths longer than
+    old_ctx / low_freq_factor are divided by factor, shorter than old_ctx / high_freq_factor kept,
+    the band in between interpolated).  Both return attention_factor 1."""
+    if not rs:
+        return inv_freq
+    kind = rs.get("rope_type", rs.get("type", "default"))
+    if kind == "default":
+        return inv_freq
+    if kind == "linear":
+        return inv_freq / rs["factor"]
+    if kind != "llama3":
+        raise NotImplementedError(kind)
+    factor, lo, hi = rs["factor"], rs["low_freq_factor"], rs["high_freq_factor"]
+    old = rs["original_max_position_embeddings"]
+    wavelen = 2 * math.pi / inv_freq
+    scaled = torch.where(wavelen > old / lo, inv_freq / factor, inv_freq)
+    smooth = (old / wavelen - lo) / (hi - lo)
+    mid = (1 - smooth) * scaled / factor + smooth * scaled
+    medium = ~(wavelen < old / hi) & ~(wavelen > old / lo)
+    return torch.where(medium, mid, scaled)
 
 
 def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:

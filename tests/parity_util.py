@@ -47,3 +47,26 @@ def check_stream(w: orc.OracleWeights, prompt: Sequence[int], oracle_tokens: Seq
         flips.append(gap)
         start = start + j + 1
     return len(flips), flips
+
+
+def usable_cpus() -> int:
+    """CPUs this process may really use (affinity mask capped by the cgroup quota): a GPU box can
+    show 128 cores to a container throttled to 16, and 128 OpenMP threads are then far slower."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt[0] != "max":
+            n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def set_oracle_threads() -> int:
+    n = min(32, usable_cpus())
+    torch.set_num_threads(n)
+    return n

@@ -26,14 +26,14 @@ def test_library_exports_every_symbol():
     lib = _lib.load()
     for name in _header_symbols():
         assert hasattr(lib, name), name
-    assert lib.lsk_abi_version() == 1
+    assert lib.lsk_abi_version() == 2
     assert isinstance(lib.lsk_last_error(), bytes)
 
 
 def test_struct_sizes_match_the_header():
     import ctypes as C
     from layerskip_b200 import _lib
-    assert C.sizeof(_lib.lsk_config) == 14 * 4
+    assert C.sizeof(_lib.lsk_config) == 19 * 4
     assert C.sizeof(_lib.lsk_round_out) == 4 * 4 + 3 * 16 * 4
     assert C.sizeof(_lib.lsk_weight_desc) == 32
     assert C.sizeof(_lib.lsk_generation) == 72      # 60 bytes of 32-bit fields, pad to 8, uint64 seed
@@ -79,13 +79,13 @@ def test_create_fails_cleanly_without_a_gpu_and_validates_arguments():
     def cfg(**over):
         base = dict(vocab=512, hidden=256, inter=704, n_layers=2, n_heads=2, n_kv_heads=2,
                     head_dim=128, rms_eps=1e-5, rope_theta=1e4, max_ctx=128, tp_rank=0, tp_size=1,
-                    attn_splits=0, flags=0)
+                    attn_splits=0, flags=0, rope_scaling=0, rope_factor=1.0)
         base.update(over)
         return _lib.lsk_config(**base)
 
-    for bad, needle in ((dict(head_dim=64), "head_dim"), (dict(tp_rank=2, tp_size=2), "tp_rank"),
+    for bad, needle in ((dict(head_dim=96), "head_dim"), (dict(tp_rank=2, tp_size=2), "tp_rank"),
                         (dict(n_heads=3), "heads"), (dict(hidden=8200), "hidden"),
-                        (dict(inter=700), "intermediate"), (dict(max_ctx=1), "max_ctx"),
+                        (dict(inter=700), "intermediate"), (dict(rope_scaling=2, rope_factor=0.0), "rope"), (dict(max_ctx=1), "max_ctx"),
                         (dict(vocab=511, tp_size=2), "vocab")):
         h = C.c_void_p()
         c = cfg(**bad)

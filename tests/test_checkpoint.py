@@ -105,11 +105,38 @@ def test_config_spellings():
     del mha["num_key_value_heads"], mha["head_dim"]
     a = arch_from_config_json(mha)[0]
     assert a.kv_heads == ARCH.heads and a.head_dim == ARCH.hidden // ARCH.heads
-    for bad in ({"rope_scaling": {"rope_type": "llama3", "factor": 8.0}},
-                {"rope_scaling": {"type": "linear", "factor": 2.0}},
+    # RoPE scaling rules, transformers-4 spelling (`rope_scaling`, keys `rope_type` or `type`) and
+    # transformers-5 spelling (`rope_parameters`)
+    l3 = {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+          "original_max_position_embeddings": 8192}
+    a = arch_from_config_json({**base, "rope_scaling": l3})[0]
+    assert (a.rope_scaling, a.rope_factor, a.rope_high_freq_factor, a.rope_original_max_pos) == \
+        ("llama3", 32.0, 4.0, 8192)
+    assert arch_from_config_json({**v5, "rope_parameters": {**l3, "rope_theta": 50000.0}})[0] == a
+    lin = arch_from_config_json({**base, "rope_scaling": {"type": "linear", "factor": 2.0}})[0]
+    assert (lin.rope_scaling, lin.rope_factor) == ("linear", 2.0)
+    for bad in ({"rope_scaling": {"rope_type": "yarn", "factor": 8.0}},
+                {"rope_scaling": {"type": "dynamic", "factor": 2.0}},
                 {"model_type": "mistral"}, {"attention_bias": True}):
         with pytest.raises(CheckpointError):
             arch_from_config_json({**base, **bad})
+
+
+def test_hf_model_config_with_transformers4_rope_scaling_is_not_silently_unscaled():
+    """a 4.x-style config object carries llama3 scaling in `cfg.rope_scaling`, not in
+    `rope_parameters`; it must reach the engine's RoPE table (or be refused), never be ignored."""
+    from layerskip_b200.weights import LlamaArch
+    cfg = type("Cfg", (), dict(
+        vocab_size=128256, hidden_size=2048, intermediate_size=8192, num_hidden_layers=16,
+        num_attention_heads=32, num_key_value_heads=8, head_dim=64, rms_norm_eps=1e-5,
+        rope_theta=500000.0,
+        rope_scaling={"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0,
+                      "high_freq_factor": 4.0, "original_max_position_embeddings": 8192}))()
+    a = LlamaArch.from_hf_config(cfg)
+    assert a == ARCHS["llama3.2-1b"]
+    cfg.rope_scaling = {"type": "yarn", "factor": 4.0}
+    with pytest.raises(NotImplementedError):
+        LlamaArch.from_hf_config(cfg)
 
 
 def test_named_archs_survive_config_json():

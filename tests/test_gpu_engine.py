@@ -211,23 +211,3 @@ def test_unsupported_inputs_fail_loudly(strategies):
     with pytest.raises(NotImplementedError):
         spec.generate_token_ids(model, case["prompt"], case["eos"], _gen_cfg(case),
                                 logits_processors=[lambda i, s: s])
-
-
-@pytest.mark.parametrize("name", ["gqa128_a0.05_long", "mha128_a0.1", "mha128_a0_full"])
-def test_megakernel_equals_multi_kernel_path(name):
-    """The persistent step megakernel runs the same device functions as the one-kernel-per-op
-    path: tokens, per-round traces and the residual rows must be bit-identical."""
-    from layerskip_b200.strategy import B200SelfSpeculativeGenerationStrategy
-    case = next(c for c in gu.spec_cases() if c["name"] == name)
-    dims, model, w = _model_for(case)
-    outs = []
-    for mega in (True, False):
-        strat = B200SelfSpeculativeGenerationStrategy(max_ctx=512, use_megakernel=mega)
-        res = strat.generate_token_ids(model, case["prompt"], case["eos"], _gen_cfg(case))
-        hidden = strat.engine_for(model).debug_hidden(8)
-        outs.append((res.predicted_tokens, [(r.n_drafted, r.n_matches, r.emitted) for r in strat.last_rounds],
-                     hidden))
-        strat.engines.close()
-    assert outs[0][0] == outs[1][0]
-    assert outs[0][1] == outs[1][1]
-    assert torch.equal(outs[0][2], outs[1][2])

@@ -1,0 +1,179 @@
+"""GPU parity at BASELINE widths: engines with the hidden / head / FFN / vocab
+sizes of Llama-2-7B, Llama-3-8B, Llama-2-13B, Llama-2-70B and llama3.2-1B (two layers deep so
+the fp32 CPU oracle stays cheap) against
+
+  (a) the oracle's teacher-forced logits (`oracle.step_all_layers`) on the same seeded weights, and
+  (b) tests/golden/shape_parity.json — logits the UNMODIFIED reference's `forward`
+      (llama_model_utils.py:155-209) produced for the same weights and ids (oracle/gen_golden_shapes.py)
+
+at contexts 70 / 520 / 1100 (1, 2 and 3 key groups per attention split) for blocks of 1, 7 and 9
+rows (the draft step, the D=6 verify block and the 16-row kernels), through the C ABI
+(`lsk_prefill` + `lsk_debug_forward_rows`).  A second test lets the engine speculate on its own at
+those widths and checks every verify row against the oracle.
+
+Tolerance: the engine computes in bf16 with fp32 accumulation, the oracle in fp32.  The bound is
+stated per test as a fraction of the logit scale (max |logit| of the block): bf16 activations
+carry 2^-9 relative rounding per stage, ~10 stages deep."""
+import pytest
+import torch
+
+from oracle import llama_oracle as orc
+from tests import golden_util as gu
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+LLAMA3_SCALING = {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0,
+                  "high_freq_factor": 4.0, "original_max_position_embeddings": 8192}
+# widths without a golden entry (too heavy for the generator's CPU): oracle-only
+EXTRA_WIDTHS = {
+    "w70b": dict(dims=(32000, 8192, 28672, 2, 64, 8, 128), rope_theta=10000.0, rope_scaling=None,
+                 tied=False, weight_seed=15),
+}
+REL_TOL = 0.012          # max |delta logit| <= REL_TOL * max |logit|  (measured: see DESIGN.md §7)
+
+
+def _golden(name):
+    for c in gu.load("shape_parity.json")["cases"]:
+        if c["name"] == name:
+            return c
+    return None
+
+
+def _spec(name):
+    return _golden(name) or {**EXTRA_WIDTHS[name], "name": name}
+
+
+def _dims(spec):
+    v, h, i, l, nh, nkv, hd = spec["dims"]
+    return orc.LlamaDims(vocab=v, hidden=h, inter=i, layers=l, heads=nh, kv_heads=nkv, head_dim=hd,
+                         rms_eps=1e-5, rope_theta=spec["rope_theta"], rope_scaling=spec["rope_scaling"])
+
+
+class _Model:
+    def __init__(self, dims, sd):
+        self._sd = sd
+        self.config = type("Cfg", (), dict(
+            vocab_size=dims.vocab, hidden_size=dims.hidden, intermediate_size=dims.inter,
+            num_hidden_layers=dims.layers, num_attention_heads=dims.heads,
+            num_key_value_heads=dims.kv_heads, head_dim=dims.head_dim, rms_norm_eps=dims.rms_eps,
+            rope_theta=dims.rope_theta, rope_scaling=dims.rope_scaling))()
+
+    def state_dict(self):
+        return self._sd
+
+
+_cache = {}
+
+
+def _setup(name):
+    """(spec, dims, engine, oracle weights, ids, oracle logits [seq, V]) — built once per width."""
+    if name in _cache:
+        return _cache[name]
+    for k in list(_cache):                       # one width resident at a time (host RAM, HBM)
+        _cache.pop(k)[2].close()
+    from layerskip_b200.engine import Engine
+    from layerskip_b200.weights import LlamaArch
+    spec = _spec(name)
+    dims = _dims(spec)
+    sd = orc.random_state_dict(dims, spec["weight_seed"])
+    if spec["tied"]:
+        sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    if "weights_checksum" in spec:
+        assert gu.checksum(sd) == spec["weights_checksum"], "seeded weights differ from the golden run"
+    w = orc.weights_from_state_dict(dims, sd)
+    model = _Model(dims, sd)
+    eng = Engine(LlamaArch.from_hf_config(model.config), max_ctx=1280, keep_logits=True)
+    eng.load_model(model)
+    contexts = spec.get("contexts", [70, 520])
+    seq_len = contexts[-1] + 9
+    g = torch.Generator().manual_seed(1000 + spec["weight_seed"])
+    ids = torch.randint(3, dims.vocab - 1, (spec.get("seq_len", seq_len),), generator=g).tolist()[:seq_len]
+    pu.set_oracle_threads()
+    with torch.inference_mode():
+        logits = orc.step_all_layers(w, ids, orc.KVStore(dims.layers))
+    _cache[name] = (spec, dims, eng, w, ids, logits, contexts)
+    return _cache[name]
+
+
+def _rows_allowed(eng_hidden):
+    return (1, 7, 9) if eng_hidden <= 4096 else (1, 7, 8)     # hidden > 4096: 8-row kernels only
+
+
+@pytest.mark.parametrize("name", ["w7b", "w8b", "w13b", "l32_1b", "w70b"])
+def test_engine_matches_oracle_and_reference_golden_at_baseline_width(name):
+    _check_teacher_forced(name)
+    if name in ("w7b", "w8b", "w13b", "l32_1b"):
+        _check_speculation_round(name)
+    _cache.pop(name)[2].close()
+
+
+def _check_teacher_forced(name):
+    spec, dims, eng, w, ids, want_all, contexts = _setup(name)
+    gold = _golden(name)
+    worst = 0.0
+    for ctx in contexts:
+        for m in _rows_allowed(dims.hidden):
+            eng.begin(exit_layer=-1, max_steps=8, eos_token_ids=[dims.vocab - 1])
+            eng.prefill(ids[:ctx + 1])                         # kv_len = ctx, pending ids[ctx]
+            assert eng.kv_len == ctx
+            got = eng.debug_forward_rows(ids[ctx:ctx + m])     # row j: after ids[:ctx+1+j]
+            want = want_all[ctx:ctx + m]
+            scale = float(want.abs().max())
+            err = float((got - want).abs().max())
+            worst = max(worst, err / scale)
+            assert torch.isfinite(got).all()
+            assert err <= REL_TOL * scale, (name, ctx, m, err, scale)
+            # arg-max agrees unless the oracle's own top-2 margin is inside the error bound
+            for j in range(m):
+                a, b = int(got[j].argmax()), int(want[j].argmax())
+                assert a == b or float(want[j][b] - want[j][a]) <= 2 * REL_TOL * scale
+            if gold is not None:                               # the unmodified reference's numbers
+                rows = gold["rows"][str(ctx)]
+                cols = torch.tensor(gold["sampled_columns"])
+                ref = torch.tensor(rows["sampled"][:m])
+                assert float((got[:, cols] - ref).abs().max()) <= REL_TOL * scale
+                lse = torch.logsumexp(got.double(), -1)
+                assert float((lse - torch.tensor(rows["logsumexp"][:m]).double()).abs().max()) <= REL_TOL * scale
+            # the same rows one at a time (m = 1 kernels) are BIT-identical to the block (batch invariance)
+            if m == 7:
+                eng.begin(exit_layer=-1, max_steps=8, eos_token_ids=[dims.vocab - 1])
+                eng.prefill(ids[:ctx + 1])
+                one = eng.debug_forward_rows(ids[ctx:ctx + 1])
+                assert torch.equal(one[0], got[0])
+    print(f"{name}: worst max|dlogit| / max|logit| = {worst:.5f}")
+
+
+def _check_speculation_round(name):
+    """The engine drafts with layer 0 (E = 1) and verifies with both layers at ctx 520 and 1100;
+    every verify row must match the oracle's teacher-forced logits on the engine's own drafts, the
+    emitted tokens must obey the accept rule, and the round must equal autoregressive decoding."""
+    spec, dims, eng, w, ids, _, contexts = _setup(name)
+    d = 6
+    for ctx in contexts[1:]:
+        eng.begin(exit_layer=1, max_steps=64, eos_token_ids=[dims.vocab - 1])
+        eng.prefill(ids[:ctx + 1])
+        r = eng.round(d)
+        got = eng.debug_logits(len(r.draft) + 1)
+        fed = ids[:ctx + 1] + r.draft
+        with torch.inference_mode():
+            want = orc.step_all_layers(w, fed, orc.KVStore(dims.layers))[ctx:]
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= REL_TOL * scale
+        assert r.verified == [int(t) for t in got.argmax(-1)]
+        n = 0
+        while n < len(r.draft) and r.draft[n] == r.verified[n]:
+            n += 1
+        assert r.n_matches == n and r.emitted == r.draft[:n] + [r.verified[n]]
+        assert r.kv_len == ctx + n + 1
+        # draft tokens = arg-max of the early-exit head (margin-gated against the oracle)
+        with torch.inference_mode():
+            early = orc.early_exit_logits(w, ids[:ctx + 1], r.draft + [0], 1)
+        for j, tok in enumerate(r.draft):
+            best = int(early[j].argmax())
+            assert tok == best or float(early[j][best] - early[j][tok]) <= 2 * REL_TOL * float(early[j].abs().max())
+        # same engine, autoregressive: identical tokens (exact)
+        eng.begin(exit_layer=-1, max_steps=64, eos_token_ids=[dims.vocab - 1])
+        eng.prefill(ids[:ctx + 1])
+        ar = [eng.ar_step() for _ in range(len(r.emitted))]
+        assert ar == r.emitted

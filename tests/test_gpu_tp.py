@@ -18,7 +18,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, case_names, q, oneshot=False):
+def _worker(rank, world, port, case_names, q, oneshot=1):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -32,10 +32,10 @@ def _worker(rank, world, port, case_names, q, oneshot=False):
         from tests import golden_util as gu
         from tests import parity_util as pu
         from tests.test_gpu_engine import _Model
-        if oneshot == 2:                                  # push fused into the GEMM epilogue
-            os.environ["LSK_TP_ONESHOT"] = "2"
-        spec = B200SelfSpeculativeGenerationStrategy(max_ctx=512, tp_rank=rank, tp_size=world,
-                                                     tp_oneshot=bool(oneshot))
+        # 0: NCCL, 1: LL push + reduce kernel (default), 2: LL push fused into the GEMM epilogue,
+        # 3: fence + flag protocol
+        os.environ["LSK_TP_ONESHOT"] = str(int(oneshot))
+        spec = B200SelfSpeculativeGenerationStrategy(max_ctx=512, tp_rank=rank, tp_size=world)
         ar = B200AutoRegressiveGenerationStrategy(engine_cache=spec.engines)
         out = {}
         for name in case_names:
@@ -61,7 +61,7 @@ def _worker(rank, world, port, case_names, q, oneshot=False):
         dist.destroy_process_group()
 
 
-def _run(names, oneshot=False, world=2):
+def _run(names, oneshot=1, world=2):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -93,15 +93,12 @@ def test_tensor_parallel_2gpu_matches_reference_and_is_self_consistent():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.skipif(not os.environ.get("LSK_TEST_EXPERIMENTAL"),
-                    reason="one-shot peer collectives were written after the round's GPU budget ran "
-                           "out; enable with LSK_TEST_EXPERIMENTAL=1")
 def test_oneshot_peer_collectives_equal_the_nccl_path():
     """csrc/tp_peer.cuh: with two ranks the rank-ordered sum a + b is bit-identical to NCCL's, so
     the whole token stream must be identical, not merely within the margin gate."""
     names = ["gqa128_a0.1", "mha128_a0.1"]
-    nccl = _run(names, oneshot=False)
-    for mode in (1, 2):                      # 1: push kernel after the GEMM, 2: push in its epilogue
+    nccl = _run(names, oneshot=0)
+    for mode in (1, 2, 3):                   # LL kernel (default), LL push in the GEMM epilogue, fence + flag
         peer = _run(names, oneshot=mode)
         for name in names:
             assert peer[0][name]["spec"] == peer[1][name]["spec"], mode
@@ -139,9 +136,6 @@ def _sample_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.skipif(not os.environ.get("LSK_TEST_EXPERIMENTAL"),
-                    reason="sampling under TP was written after the round's GPU budget ran out; "
-                           "enable with LSK_TEST_EXPERIMENTAL=1")
 def test_sampling_under_tensor_parallelism_keeps_ranks_in_lockstep():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

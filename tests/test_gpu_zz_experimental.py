@@ -28,18 +28,6 @@ def _generate(case, **engine_kwargs):
     return r.predicted_tokens, r.acceptance_rate, rounds
 
 
-@pytest.mark.parametrize("name", ["gqa128_a0.1", "mha128_a0.1", "gqa128_a0.05_long"])
-def test_push_merge_attention_is_bit_identical_to_the_pull_merge_kernel(name, monkeypatch):
-    """attn_cluster_push_kernel: same partials, same merge arithmetic and order — only the
-    direction of the distributed-shared-memory exchange differs, so every round must be equal."""
-    case = next(c for c in gu.spec_cases() if c["name"] == name)
-    monkeypatch.delenv("LSK_ATTN_PUSH", raising=False)
-    want = _generate(case)
-    monkeypatch.setenv("LSK_ATTN_PUSH", "1")
-    got = _generate(case)
-    assert got == want
-
-
 @pytest.mark.parametrize("n,k,m", [(256, 256, 1), (1000, 512, 7), (32000, 4096, 7), (32000, 4096, 16),
                                    (16032, 5120, 1)])
 def test_tcgen05_lm_head_matches_a_torch_reference(n, k, m):

@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the acceptance sweep / AR legs")
     ap.add_argument("--cpu-max-steps", type=int, default=0, help="reference arm: tokens per step")
+    ap.add_argument("--cpu-budget", type=float, default=300.0,
+                    help="reference arm: seconds of CPU time the K timed generations may take in total")
     return ap.parse_args()
 
 
@@ -223,16 +225,32 @@ def cpu_reference_run(args, w, arch, prompts, n_generations, max_steps):
     return tokens, seconds, sum(rates) / max(1, len(rates))
 
 
-def cpu_sized_sample(args, w, arch, prompts, budget_s):
-    """Pick a continuation length so one generation costs about `budget_s` of CPU time:
-    probe with 2 tokens (prefill + 1-2 rounds), then extrapolate the per-round cost."""
+def cpu_probe(args, w, arch, prompts):
+    """Prefill cost and per-round cost of the CPU implementation, from two short generations
+    (2 and 6 tokens): seconds(n) = prefill + rounds(n) * per_round.  Doubles as warm-up."""
     t0 = time.perf_counter()
     cpu_reference_run(args, w, arch, prompts, 1, 2)
-    probe = time.perf_counter() - t0
-    # a 2-token probe is prefill + <= 2 rounds; assume half of it is per-round cost (upper bound)
-    per_round = max(probe / 4, 1e-3)
-    n = int(max(2, min(64, (budget_s - probe) / per_round)))
-    return n, probe
+    t2 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cpu_reference_run(args, w, arch, prompts, 1, 6)
+    t6 = time.perf_counter() - t0
+    per_round = max((t6 - t2) / 4.0, 1e-4)             # acceptance ~0 on random init: 1 token per round
+    prefill = max(t2 - 2 * per_round, 0.0)
+    return prefill, per_round, t2 + t6
+
+
+def cpu_sized_sample(args, w, arch, prompts, budget_s):
+    """Continuation length so that ONE generation costs about `budget_s` of CPU time, between 16
+    tokens (below that the prefill dominates the rate) and 64."""
+    prefill, per_round, spent = cpu_probe(args, w, arch, prompts)
+    n = int(max(16, min(64, (budget_s - prefill) / per_round)))
+    return n, spent, prefill, per_round
+
+
+def workload_string(args):
+    return (f"{args.arch} arch, random-init (alpha={args.alpha}), exit_layer={args.exit_layer}, "
+            f"num_speculations={args.num_speculations}, greedy, {args.prompt_len}-id synthetic prompts, "
+            f"{args.max_steps}-token continuations")
 
 
 def cpu_model_name():
@@ -261,30 +279,39 @@ def run_reference_arm(args):
     cores = cpu_threads()
     w, w_dtype = cpu_weights(sd, arch)
     del sd
-    budget = 100.0 / max(1, args.steps)           # whole arm: under two minutes of CPU time
+    # bounded sample of the SAME workload (same architecture, weights, prompts, exit layer, draft
+    # count, greedy): the 512-token continuation is cut to 16..64 tokens so that the whole
+    # --steps K run stays within --cpu-budget seconds of CPU time
+    steps = max(1, args.steps)
     try:
-        with time_limit(170):
-            cpu_steps, _probe = cpu_sized_sample(args, w, arch, prompts, budget)   # doubles as warm-up
+        with time_limit(args.cpu_budget + 240):
+            cpu_steps, _spent, prefill_s, round_s = cpu_sized_sample(args, w, arch, prompts, args.cpu_budget / steps)
             if args.cpu_max_steps:
                 cpu_steps = args.cpu_max_steps
-            tokens, seconds, acc = cpu_reference_run(args, w, arch, prompts, max(1, args.steps), cpu_steps)
+            tokens, seconds, acc = cpu_reference_run(args, w, arch, prompts, steps, cpu_steps)
     except TimeoutError as exc:
         emit(json.dumps({"impl": "reference", "unavailable": f"CPU run did not finish: {exc}"}))
         return
     value = tokens / seconds
+    full = args.max_steps / (prefill_s + args.max_steps * round_s)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / max(1, args.steps) * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{w_dtype} (CPU oracle port; the engine arm computes in bf16)",
         "data": "synthetic",
-        "config": {"workload": f"{args.arch} random-init alpha={args.alpha}, exit_layer={args.exit_layer}, "
-                               f"num_speculations={args.num_speculations}, greedy, prompt {args.prompt_len} ids",
-                   "sample": f"{cpu_steps}-token continuations (prefill of {args.prompt_len} ids included)"},
+        "config": {"workload": workload_string(args),
+                   "sample": f"each step = one generation cut to a {cpu_steps}-token continuation "
+                             f"(prefill of {args.prompt_len} ids included); measured prefill {prefill_s:.2f} s, "
+                             f"{round_s * 1e3:.0f} ms per round -> {full:.2f} tokens/s extrapolated to the full "
+                             f"{args.max_steps}-token continuation"},
         "acceptance_rate": acc,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "cpu": cpu_model_name(),
-                         "sample": f"{max(1, args.steps)} generations x {cpu_steps} tokens, "
-                                   f"prompt {args.prompt_len}, oracle port in torch {w_dtype} on {cores} threads"},
+                         "sample": f"{steps} generations x {cpu_steps} tokens, "
+                                   f"prompt {args.prompt_len}, oracle port in torch {w_dtype} on {cores} threads",
+                         "prefill_s": prefill_s, "s_per_round": round_s,
+                         "extrapolated_full_length_tokens_per_s": full},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
@@ -638,9 +665,7 @@ def run_b200_arm(args):
         "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "acceptance_rate": acc_mean,
-        "config": {"workload": f"{args.arch} arch, random-init (alpha={args.alpha}), "
-                               f"exit_layer={args.exit_layer}, num_speculations={args.num_speculations}, "
-                               f"greedy, {args.prompt_len}-id synthetic prompts, {args.max_steps}-token continuations",
+        "config": {"workload": workload_string(args),
                    "parallelism": f"tp{tp}" if tp > 1 else f"replicas{world}",
                    **({"tp_collectives": {"0": "nccl", "2": "peer one-shot LL, push fused into the GEMM epilogue",
                                           "3": "peer one-shot, fence + flag"}.get(
@@ -669,13 +694,14 @@ def run_b200_arm(args):
             cores = cpu_threads()
             t0 = time.perf_counter()
             with time_limit(150):
-                n_cpu, _probe = cpu_sized_sample(args, w, arch, prompts, 30.0)
+                n_cpu, _spent, pre_s, rnd_s = cpu_sized_sample(args, w, arch, prompts, 25.0)
                 toks, secs, _acc = cpu_reference_run(args, w, arch, prompts, 1, n_cpu)
             line["cpu_baseline"] = {"value": toks / secs, "unit": UNIT, "cores": cores, "kind": "port",
                                     "cpu": cpu_model_name(),
                                     "sample": f"1 generation x {n_cpu} tokens, prompt {args.prompt_len} ids "
                                               f"(prefill included), oracle port in torch {w_dtype} on {cores} threads; "
-                                              f"{time.perf_counter() - t0:.1f} s of CPU work incl. sizing probe"}
+                                              f"{time.perf_counter() - t0:.1f} s of CPU work incl. sizing probe; "
+                                              f"prefill {pre_s:.2f} s + {rnd_s * 1e3:.0f} ms per round"}
             del w
         except Exception as exc:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port",

@@ -36,6 +36,7 @@ typedef enum {
 #define LSK_FLAG_KEEP_LOGITS 1u  /* also store fp32 logits (needed for sampling / debug reads) */
 #define LSK_FLAG_NO_PDL 2u       /* disable programmatic dependent launch                    */
 #define LSK_FLAG_NO_GRAPH 4u     /* launch kernels eagerly instead of replaying CUDA graphs  */
+#define LSK_FLAG_NO_PREFILL_TC 8u /* keep only the decode-layout weights: the prompt pass runs 16 rows at a time on the decode kernels instead of 128 rows at a time on tcgen05 (saves the second, canonical-layout weight copy) */
 #define LSK_FLAG_TP_NCCL 16u     /* tp_size > 1: use NCCL all-reduce instead of the one-shot kernels over peer-mapped HBM */
 
 /* Llama architecture + engine sizing.  Replaces what the reference reads off the HF model
@@ -163,7 +164,8 @@ typedef enum {
   LSK_DBG_KROW = 2,          /* bf16->fp32 K cache row [head_dim]: layer, index = kv_head*max_ctx + pos */
   LSK_DBG_VROW = 3,
   LSK_DBG_PROBS_DRAFT = 4,   /* fp32 [16, vocab] warped (T, top-k, top-p) draft distributions     */
-  LSK_DBG_PROBS_VERIFY = 5   /* fp32 [16, vocab] warped verifier distributions of the last round */
+  LSK_DBG_PROBS_VERIFY = 5,  /* fp32 [16, vocab] warped verifier distributions of the last round */
+  LSK_DBG_RESIDUAL = 6       /* fp32 [vocab] max(p_verify - p_draft, 0) of the last rejected draft (unnormalised; self_speculation_generator.py:27-29 max_fn before its division) */
 } lsk_debug_what;
 int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index,
                    float* dst_host, int64_t n_floats);

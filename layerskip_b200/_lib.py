@@ -16,6 +16,7 @@ LSK_MAX_EOS = 8
 LSK_FLAG_KEEP_LOGITS = 1
 LSK_FLAG_NO_PDL = 2
 LSK_FLAG_NO_GRAPH = 4
+LSK_FLAG_NO_PREFILL_TC = 8
 LSK_FLAG_TP_NCCL = 16
 LSK_ROPE_DEFAULT, LSK_ROPE_LINEAR, LSK_ROPE_LLAMA3 = 0, 1, 2
 
@@ -23,7 +24,7 @@ LSK_ROPE_DEFAULT, LSK_ROPE_LINEAR, LSK_ROPE_LLAMA3 = 0, 1, 2
  LSK_W_LN2, LSK_W_GATE, LSK_W_UP, LSK_W_DOWN) = range(12)
 
 LSK_DBG_HIDDEN, LSK_DBG_LOGITS, LSK_DBG_KROW, LSK_DBG_VROW, LSK_DBG_PROBS_DRAFT, \
-    LSK_DBG_PROBS_VERIFY = range(6)
+    LSK_DBG_PROBS_VERIFY, LSK_DBG_RESIDUAL = range(7)
 
 
 class LskLibraryError(RuntimeError):

@@ -28,7 +28,7 @@ namespace cg = cooperative_groups;
 
 constexpr int kAttnThreads = 128;
 constexpr int kKeyGroup = 64;                 // keys per pipeline stage (== one KV page)
-constexpr int kAttnStages = 2;                // K/V stages in flight per CTA
+constexpr int kAttnMaxStages = 4;             // K/V stages in flight per CTA (AttnArgs::n_stages of them used)
 constexpr int kAttnHeader = 128;              // mbarriers
 constexpr int kMaxSplits = 8;                 // portable cluster size
 
@@ -51,15 +51,18 @@ struct AttnArgs {
   int merge_off;               // byte offset of the warp-merge buffer (== stage 0 when aliased)
   int part_off;                // byte offset of this CTA's partial (O, then m/l)
   int reload_per_rb;           // 1: the merge buffer aliases the stages -> K/V re-fetched per row block
+  int out_canon;               // 1: `out` is a canonical K-major operand (rows = tokens) for prefill_tc.cuh
+  int n_stages;                // K/V ring depth (2 .. kAttnMaxStages)
 };
 
 // shared-memory plan of one launch (host and device agree through AttnArgs offsets)
 struct AttnSmemPlan {
-  int merge_off, part_off, reload_per_rb;
+  int merge_off, part_off, reload_per_rb, n_stages;
   size_t total;
 };
-__host__ inline AttnSmemPlan attn_smem_plan(int hd, int group, int M) {
+__host__ inline AttnSmemPlan attn_smem_plan(int hd, int group, int M, int kAttnStages = 2) {
   AttnSmemPlan p;
+  p.n_stages = kAttnStages;
   const int R = group * M;
   const int rows_pad = (R + 15) / 16 * 16;
   const int stage_bytes = 2 * kKeyGroup * hd * 2;
@@ -119,6 +122,19 @@ __device__ __forceinline__ void merge_splits_write(const AttnArgs& a, int kvh, i
   }
   const float inv = 1.f / ll;
   const int tok = row / a.group, hq = kvh * a.group + row % a.group;
+  if (a.out_canon) {           // two 16-byte chunks of the O projection's B operand
+    unsigned char* base = reinterpret_cast<unsigned char*>(a.out);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint4 v;
+      v.x = pack_bf16x2(acc[8 * c] * inv, acc[8 * c + 1] * inv);
+      v.y = pack_bf16x2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv);
+      v.z = pack_bf16x2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv);
+      v.w = pack_bf16x2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv);
+      *reinterpret_cast<uint4*>(base + canon_offset(tok, hq * HD + dseg + 8 * c)) = v;
+    }
+    return;
+  }
   __nv_bfloat16* op = a.out + (size_t)tok * a.out_ld + hq * HD + dseg;
 #pragma unroll
   for (int i = 0; i < 16; i += 2)
@@ -136,8 +152,9 @@ attn_cluster_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   cg::cluster_group cluster = cg::this_cluster();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(dsm);
-  uint64_t* empty_bar = full_bar + kAttnStages;
+  uint64_t* empty_bar = full_bar + kAttnMaxStages;
   unsigned char* stages = dsm + kAttnHeader;
+  const int kAttnStages = a.n_stages;
   float* mo = reinterpret_cast<float*>(dsm + a.merge_off);       // [4 warps][16 rows][HD]
   float* mml = mo + 4 * 16 * HD;                                  // [4][16][2]
   float* po = reinterpret_cast<float*>(dsm + a.part_off);        // [rows_pad][HD]
@@ -163,7 +180,6 @@ attn_cluster_kernel(const AttnArgs a) {
   const int R = a.group * a.M;                       // real query rows (token-major)
   const int n_rb = (R + 15) / 16;
   const bool reload = a.reload_per_rb != 0 || n_mine > kAttnStages;   // K/V re-fetched per row block
-  const int n_items = reload ? n_rb * n_mine : n_mine;               // bulk-copy items, in consumption order
   int issued = 0;                                                    // (thread 0) items handed to the TMA engine
 
   auto issue = [&](int item) {       // thread 0 only

@@ -116,6 +116,17 @@ __host__ __device__ __forceinline__ size_t kv_elem_offset(int hd, int page, int 
   return ((size_t)(page * n_kv_heads + head) * kPageTokens + tok) * hd + chunk * 8 + (d & 7);
 }
 
+// ---------------------------------------------------------------------------------------
+// Canonical K-major operand layout of the tcgen05 kernels (prefill_tc.cuh, lmhead_tc.cuh):
+// stages of 128 rows x 64 k (16 KiB) made of 8-row x 16-byte core matrices,
+// core(row group i, k chunk j) at (i*8 + j)*128 B.  Byte offset of element (row < 128, k):
+// ---------------------------------------------------------------------------------------
+constexpr int kCanonStageBytes = 128 * 64 * 2;
+__host__ __device__ __forceinline__ size_t canon_offset(int row, int k) {
+  const int s = k >> 6, j = (k >> 3) & 7, i = row >> 3, r = row & 7;
+  return (size_t)s * kCanonStageBytes + (size_t)(i * 8 + j) * 128 + r * 16 + (k & 7) * 2;
+}
+
 // Device-resident generation state (one per engine).  `tok[0]` is the pending input token,
 // `tok[1 + i]` the i-th draft token of the current round.
 struct DevState {

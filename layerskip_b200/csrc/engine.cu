@@ -23,6 +23,7 @@
 #include "gemm_skinny.cuh"
 #include "tp_peer.cuh"
 #include "lmhead_tc.cuh"
+#include "prefill_tc.cuh"
 #include "misc_kernels.cuh"
 #include "sampling.cuh"
 
@@ -75,6 +76,11 @@ struct LayerWeights {
   __nv_bfloat16* wd = nullptr;    // packed [hidden, inter_l]
   __nv_bfloat16* ln1 = nullptr;
   __nv_bfloat16* ln2 = nullptr;
+  // tcgen05 prefill (prefill_tc.cuh): second copy in the canonical K-major tile layout
+  unsigned char* wqkv_c = nullptr;
+  unsigned char* wo_c = nullptr;
+  unsigned char* wgu_c = nullptr;
+  unsigned char* wd_c = nullptr;
   unsigned loaded = 0;            // bit per role
 };
 
@@ -89,6 +95,7 @@ struct lsk_engine {
   int heads_l = 0, kv_heads_l = 0, q_rows = 0, kv_rows = 0, inter_l = 0, vocab_l = 0,
       vocab_l_pad = 0, vocab_off = 0, group = 0, inter_l_pad = 0;
   int n_pages = 0, max_pos = 0, n_splits = 0;
+  int attn_stages = 4;                 // K/V ring depth of the attention kernel (LSK_ATTN_STAGES, 2..4)
   int max_rows = kMaxRows;             // token rows one step can carry (8 when 16 do not fit)
   bool use_pdl = true, use_graph = true, keep_logits = false;
 
@@ -101,6 +108,17 @@ struct lsk_engine {
   unsigned char* lm_head_tc = nullptr;   // [lm_tc_tiles][hidden / 64][16 KiB]
   int lm_tc_tiles = 0, lm_tc_grid = 0, lm_tc_stages = 0;
   unsigned globals_loaded = 0;
+  // tcgen05 prefill: 128-token passes (on unless LSK_FLAG_NO_PREFILL_TC / LSK_PREFILL_TC=0)
+  bool pf_tc = false;
+  int pf_stages = 0;
+  int kst_h = 0, kst_q = 0, kst_i = 0;          // 64-wide k stages of hidden / q_rows / inter_l
+  int pf_t_qkv = 0, pf_t_h = 0, pf_t_gu = 0;     // 128-row tiles of qkv / hidden / gate-up outputs
+  float* hidden_p = nullptr;             // [128][hidden] fp32 residual rows of a prompt chunk
+  float* tp_buf_p = nullptr;             // [128][hidden] fp32 row-parallel partial sums (TP)
+  __nv_bfloat16* q_p = nullptr;          // [128][q_rows]
+  unsigned char* xn_c = nullptr;         // canonical activations: RMS-normed rows   [kst_h][16 KiB]
+  unsigned char* attn_c = nullptr;       //                        attention output   [kst_q][16 KiB]
+  unsigned char* act_c = nullptr;        //                        silu(gate) * up    [kst_i][16 KiB]
 
   __nv_bfloat16* kpool = nullptr;      // [layer][page][kv_head][64][128]
   __nv_bfloat16* vpool = nullptr;
@@ -302,6 +320,25 @@ static int ll_grid(int n2) {
   int g = (n2 + kArThreads - 1) / kArThreads;
   return g < 1 ? 1 : (g > 148 ? 148 : g);      // every CTA resident at once (spin-wait safety)
 }
+static int emit_allreduce_resid_nccl(lsk_engine* e, float* buf, float* x, int M) {
+  const lsk_config& c = e->cfg;
+  e->cur_class = CLS_COMM;
+  cudaEvent_t ea = nullptr, eb = nullptr;
+  if (e->profiling) {
+    cudaEventCreate(&ea); cudaEventCreate(&eb);
+    cudaEventRecord(ea, e->stream);
+  }
+  e->launches += 1;
+  e->capture_launches += 1;
+  NC(ncclAllReduce(buf, buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+  if (e->profiling) {
+    cudaEventRecord(eb, e->stream);
+    e->prof_events.push_back({CLS_COMM, {ea, eb}});
+  }
+  e->cur_class = CLS_MISC;
+  CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)buf, c.hidden, c.hidden));
+  return LSK_OK;
+}
 static int emit_allreduce_resid(lsk_engine* e, float* x, int M) {
   const lsk_config& c = e->cfg;
   if (e->peer_ok && e->peer_mode == 3) {
@@ -319,22 +356,7 @@ static int emit_allreduce_resid(lsk_engine* e, float* x, int M) {
               (const float*)e->tp_buf, x, n2));
     return LSK_OK;
   }
-  e->cur_class = CLS_COMM;
-  cudaEvent_t ea = nullptr, eb = nullptr;
-  if (e->profiling) {
-    cudaEventCreate(&ea); cudaEventCreate(&eb);
-    cudaEventRecord(ea, e->stream);
-  }
-  e->launches += 1;
-  e->capture_launches += 1;
-  NC(ncclAllReduce(e->tp_buf, e->tp_buf, (size_t)M * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
-  if (e->profiling) {
-    cudaEventRecord(eb, e->stream);
-    e->prof_events.push_back({CLS_COMM, {ea, eb}});
-  }
-  e->cur_class = CLS_MISC;
-  CU(launch(e, residual_add_kernel, dim3(8, M), dim3(256), 0, x, c.hidden, (const float*)e->tp_buf, c.hidden, c.hidden));
-  return LSK_OK;
+  return emit_allreduce_resid_nccl(e, e->tp_buf, x, M);
 }
 
 // Fused variant (peer_mode 2): the row-parallel GEMM pushes its tiles to every rank from its
@@ -378,7 +400,10 @@ static int launch_attention_t(lsk_engine* e, AttnArgs& a) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured.fetch_or(bit, std::memory_order_relaxed);
   }
-  const AttnSmemPlan sp = attn_smem_plan(HD, a.group, a.M);
+  int st = e->attn_stages;
+  while (st > 2 && attn_smem_plan(HD, a.group, a.M, st).total > (size_t)kSmemMax) --st;
+  const AttnSmemPlan sp = attn_smem_plan(HD, a.group, a.M, st);
+  a.n_stages = st;
   if (sp.total > (size_t)kSmemMax)
     return fail(LSK_ERR_INVALID, "attention: %d query rows per kv head do not fit shared memory", a.group * a.M);
   a.rows_pad = (a.group * a.M + 15) / 16 * 16;
@@ -386,7 +411,11 @@ static int launch_attention_t(lsk_engine* e, AttnArgs& a) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.n_kv_heads, a.n_splits);
   cfg.blockDim = dim3(kAttnThreads);
-  cfg.dynamicSmemBytes = sp.total;
+  // a grid that fits one wave gets a whole SM per CTA (> half of the SM's shared memory): the
+  // CTAs then spread over the SMs instead of sharing a few SMs' load bandwidth
+  size_t smem = sp.total;
+  if (a.n_kv_heads * a.n_splits <= e->sm_count && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = e->stream;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -501,6 +530,85 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
       a.out_f32 = e->tp_buf; a.out_ld = c.hidden;
       TRY((launch_gemm<PRO_BF16, EPI_STORE>(e, e->p_d, a)));
       TRY(emit_allreduce_resid(e, x, M));
+    }
+  }
+  return LSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prompt chunk of m <= 128 tokens at positions c0 .. c0+m-1 through every layer on the tcgen05
+// GEMMs (forward_early + forward_remainder of llama_model_utils.py:213-276 / 363-383 on s = T_p)
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+static int launch_prefill_gemm(lsk_engine* e, PrefillGemmArgs& a) {
+  a.n_stages = e->pf_stages;
+  const int grid = a.n_tiles < e->sm_count ? a.n_tiles : e->sm_count;
+  CU(launch(e, prefill_gemm_tc_kernel<EPI>, dim3(grid), dim3(kTcThreads), prefill_tc_smem_bytes(a.n_stages), a));
+  return LSK_OK;
+}
+
+static int enqueue_prefill_chunk(lsk_engine* e, int c0, int m) {
+  const lsk_config& c = e->cfg;
+  const bool tp = c.tp_size > 1;
+  e->cur_class = CLS_MISC;
+  CU(launch(e, embed_tokens_kernel, dim3(m), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+            (const int*)(e->d_prompt + c0), e->hidden_p, c.hidden));
+  // rows of one attention launch: as many as fit its shared-memory plan (multiple of 16)
+  int m_attn = 16;
+  for (int cand = kPfTokens; cand >= 16; cand -= 16)
+    if (attn_smem_plan(c.head_dim, e->group, cand).total <= (size_t)kSmemMax) { m_attn = cand; break; }
+  for (int li = 0; li < c.n_layers; ++li) {
+    LayerWeights& L = e->layers[li];
+    __nv_bfloat16* kp = e->kpool + (size_t)li * e->pool_layer_elems;
+    __nv_bfloat16* vp = e->vpool + (size_t)li * e->pool_layer_elems;
+    e->cur_class = CLS_QKV;
+    CU(launch(e, rms_canon_kernel, dim3(m), dim3(256), 0, (const float*)e->hidden_p, c.hidden,
+              (const __nv_bfloat16*)L.ln1, c.rms_eps, c.hidden, e->xn_c));
+    {
+      PrefillGemmArgs a{};
+      a.W = L.wqkv_c; a.X = e->xn_c; a.n_tiles = e->pf_t_qkv; a.n_rows = e->q_rows + 2 * e->kv_rows;
+      a.n_kst = e->kst_h; a.M = m;
+      a.q_out = e->q_p; a.q_ld = e->q_rows; a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
+      a.pos0 = c0; a.rope = e->rope; a.head_dim = c.head_dim;
+      a.q_rows = e->q_rows; a.kv_rows = e->kv_rows; a.n_kv_heads = e->kv_heads_l;
+      TRY(launch_prefill_gemm<PF_EPI_QKV>(e, a));
+    }
+    e->cur_class = CLS_ATTN;
+    for (int r0 = 0; r0 < m; r0 += m_attn) {
+      AttnArgs a{};
+      a.q = e->q_p + (size_t)r0 * e->q_rows; a.q_ld = e->q_rows;
+      // canonical rows are addressed by token index inside the 128-row operand: shift by r0 rows
+      a.out = reinterpret_cast<__nv_bfloat16*>(e->attn_c + canon_offset(r0, 0)); a.out_canon = 1;
+      a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
+      a.base_len = e->d_zero; a.pos_off = c0 + r0; a.M = (m - r0) < m_attn ? (m - r0) : m_attn;
+      a.group = e->group; a.n_kv_heads = e->kv_heads_l; a.n_splits = e->n_splits;
+      a.scale = 1.0f / sqrtf((float)c.head_dim);
+      TRY(launch_attention(e, a, c.head_dim));
+    }
+    e->cur_class = CLS_O;
+    {
+      PrefillGemmArgs a{};
+      a.W = L.wo_c; a.X = e->attn_c; a.n_tiles = e->pf_t_h; a.n_rows = c.hidden; a.n_kst = e->kst_q; a.M = m;
+      a.out_f32 = tp ? e->tp_buf_p : e->hidden_p; a.out_ld = c.hidden;
+      if (!tp) TRY(launch_prefill_gemm<PF_EPI_RESID>(e, a));
+      else { TRY(launch_prefill_gemm<PF_EPI_STORE>(e, a)); TRY(emit_allreduce_resid_nccl(e, e->tp_buf_p, e->hidden_p, m)); }
+    }
+    e->cur_class = CLS_GATEUP;
+    CU(launch(e, rms_canon_kernel, dim3(m), dim3(256), 0, (const float*)e->hidden_p, c.hidden,
+              (const __nv_bfloat16*)L.ln2, c.rms_eps, c.hidden, e->xn_c));
+    {
+      PrefillGemmArgs a{};
+      a.W = L.wgu_c; a.X = e->xn_c; a.n_tiles = e->pf_t_gu; a.n_rows = 2 * e->inter_l; a.n_kst = e->kst_h; a.M = m;
+      a.act_canon = e->act_c;
+      TRY(launch_prefill_gemm<PF_EPI_SILU>(e, a));
+    }
+    e->cur_class = CLS_DOWN;
+    {
+      PrefillGemmArgs a{};
+      a.W = L.wd_c; a.X = e->act_c; a.n_tiles = e->pf_t_h; a.n_rows = c.hidden; a.n_kst = e->kst_i; a.M = m;
+      a.out_f32 = tp ? e->tp_buf_p : e->hidden_p; a.out_ld = c.hidden;
+      if (!tp) TRY(launch_prefill_gemm<PF_EPI_RESID>(e, a));
+      else { TRY(launch_prefill_gemm<PF_EPI_STORE>(e, a)); TRY(emit_allreduce_resid_nccl(e, e->tp_buf_p, e->hidden_p, m)); }
     }
   }
   return LSK_OK;
@@ -795,10 +903,14 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->n_pages = (c.max_ctx + kPageTokens - 1) / kPageTokens;
   e->max_pos = e->n_pages * kPageTokens;
   // split-KV factor: a constant of the engine (results are batch-invariant only for a fixed
-  // partition); 8 = the portable thread-block-cluster size -> one 64-key group per CTA up to
-  // ctx 512, two up to 1024
-  e->n_splits = c.attn_splits > 0 ? c.attn_splits : 8;
+  // partition).  Measured (profiles/r2_attention_sweep.md): the kernel is bound by per-SM load
+  // bandwidth and barrier latency, so the best grid is ONE CTA per SM on as many SMs as possible —
+  // splits = floor(SMs / kv heads), at most the portable cluster size 8 (7B: 32 heads x 4 splits).
+  e->n_splits = c.attn_splits > 0 ? c.attn_splits : std::max(1, std::min(8, e->sm_count / std::max(1, e->kv_heads_l)));
   if (const char* env = getenv("LSK_ATTN_SPLITS")) e->n_splits = atoi(env);   // clamped to [1, 8] below
+  if (const char* env = getenv("LSK_ATTN_STAGES")) e->attn_stages = atoi(env);
+  if (e->attn_stages < 2) e->attn_stages = 2;
+  if (e->attn_stages > kAttnMaxStages) e->attn_stages = kAttnMaxStages;
   if (e->n_splits > 8) e->n_splits = 8;
   if (e->n_splits < 1) e->n_splits = 1;
 
@@ -826,6 +938,17 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
     }
   }
   e->max_rows = plan_sched(2, kMaxRows, PRO_RMS, EPI_QKV, e->p_qkv, e->sm_count).ok ? kMaxRows : 8;
+  {
+    const char* env = getenv("LSK_PREFILL_TC");
+    e->pf_tc = !(c.flags & LSK_FLAG_NO_PREFILL_TC) && !(env && atoi(env) == 0) && c.hidden % 64 == 0;
+    e->pf_stages = kPfMaxStages;
+    e->kst_h = c.hidden / 64;
+    e->kst_q = (e->q_rows + 63) / 64;
+    e->kst_i = (e->inter_l + 63) / 64;
+    e->pf_t_qkv = (e->q_rows + 2 * e->kv_rows + 127) / 128;
+    e->pf_t_h = (c.hidden + 127) / 128;
+    e->pf_t_gu = (2 * e->inter_l + 127) / 128;
+  }
 
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&e->ev0));
@@ -846,6 +969,24 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
     TRY(alloc((void**)&L.wd, h * e->inter_l_pad * 2));
     TRY(alloc((void**)&L.ln1, h * 2));
     TRY(alloc((void**)&L.ln2, h * 2));
+    if (e->pf_tc) {
+      TRY(alloc((void**)&L.wqkv_c, (size_t)e->pf_t_qkv * e->kst_h * kCanonStageBytes));
+      TRY(alloc((void**)&L.wo_c, (size_t)e->pf_t_h * e->kst_q * kCanonStageBytes));
+      TRY(alloc((void**)&L.wgu_c, (size_t)e->pf_t_gu * e->kst_h * kCanonStageBytes));
+      TRY(alloc((void**)&L.wd_c, (size_t)e->pf_t_h * e->kst_i * kCanonStageBytes));
+    }
+  }
+  if (e->pf_tc) {
+    TRY(alloc((void**)&e->hidden_p, (size_t)kPfTokens * h * 4));
+    TRY(alloc((void**)&e->tp_buf_p, (size_t)kPfTokens * h * 4));
+    TRY(alloc((void**)&e->q_p, (size_t)kPfTokens * e->q_rows * 2));
+    TRY(alloc((void**)&e->xn_c, (size_t)e->kst_h * kCanonStageBytes));
+    TRY(alloc((void**)&e->attn_c, (size_t)e->kst_q * kCanonStageBytes));
+    TRY(alloc((void**)&e->act_c, (size_t)e->kst_i * kCanonStageBytes));
+    CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   }
   TRY(alloc((void**)&e->embed, (size_t)c.vocab * h * 2));
   TRY(alloc((void**)&e->final_norm, h * 2));
@@ -924,6 +1065,11 @@ void lsk_destroy(lsk_engine* e) {
   if (e->comm) ncclCommDestroy(e->comm);
   for (auto& L : e->layers) {
     cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.wgu); cudaFree(L.wd); cudaFree(L.ln1); cudaFree(L.ln2);
+    cudaFree(L.wqkv_c); cudaFree(L.wo_c); cudaFree(L.wgu_c); cudaFree(L.wd_c);
+  }
+  {
+    void* pf[] = {e->hidden_p, e->tp_buf_p, e->q_p, e->xn_c, e->attn_c, e->act_c};
+    for (void* p : pf) if (p) cudaFree(p);
   }
   void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->lm_head_tc, e->kpool, e->vpool, e->page_table, e->rope,
                   e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->logits_gath, e->logits_full, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
@@ -1037,6 +1183,19 @@ static int pack(lsk_engine* e, const __nv_bfloat16* src, int64_t src_ld, int64_t
   return LSK_OK;
 }
 
+static int pack_canon(lsk_engine* e, const __nv_bfloat16* src, int64_t src_ld, int64_t row0, int64_t col0,
+                      int64_t n_rows, int64_t K, unsigned char* dst, int64_t dst_row0, int mode, int n_kst) {
+  if (!e->pf_tc) return LSK_OK;
+  const int64_t total = n_rows * (K / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  pack_canonical_rows_kernel<<<blocks, 256, 0, e->stream>>>(src, src_ld, row0, col0, n_rows, K, dst, dst_row0, mode,
+                                                            n_kst, e->cfg.head_dim);
+  CU(cudaGetLastError());
+  return LSK_OK;
+}
+
 int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n) {
   if (!e || !descs) return fail(LSK_ERR_INVALID, "null argument");
   const lsk_config& c = e->cfg;
@@ -1086,30 +1245,37 @@ int lsk_load_weights(lsk_engine* e, const lsk_weight_desc* descs, int32_t n) {
       case LSK_W_Q:
         TRY(expect(qd, h));
         TRY(pack(e, src, h, (int64_t)r * e->q_rows, 0, e->q_rows, h, L->wqkv, 0, MAP_ROPE_HEADS));
+        TRY(pack_canon(e, src, h, (int64_t)r * e->q_rows, 0, e->q_rows, h, L->wqkv_c, 0, MAP_ROPE_HEADS, e->kst_h));
         break;
       case LSK_W_K:
         TRY(expect(kvd, h));
         TRY(pack(e, src, h, (int64_t)r * e->kv_rows, 0, e->kv_rows, h, L->wqkv, e->q_rows, MAP_ROPE_HEADS));
+        TRY(pack_canon(e, src, h, (int64_t)r * e->kv_rows, 0, e->kv_rows, h, L->wqkv_c, e->q_rows, MAP_ROPE_HEADS, e->kst_h));
         break;
       case LSK_W_V:
         TRY(expect(kvd, h));
         TRY(pack(e, src, h, (int64_t)r * e->kv_rows, 0, e->kv_rows, h, L->wqkv, e->q_rows + e->kv_rows, MAP_PLAIN));
+        TRY(pack_canon(e, src, h, (int64_t)r * e->kv_rows, 0, e->kv_rows, h, L->wqkv_c, e->q_rows + e->kv_rows, MAP_PLAIN, e->kst_h));
         break;
       case LSK_W_O:   // row-parallel: this rank's input features = its heads
         TRY(expect(h, qd));
         TRY(pack(e, src, qd, 0, (int64_t)r * e->q_rows, h, e->q_rows, L->wo, 0, MAP_PLAIN));
+        TRY(pack_canon(e, src, qd, 0, (int64_t)r * e->q_rows, h, e->q_rows, L->wo_c, 0, MAP_PLAIN, e->kst_q));
         break;
       case LSK_W_GATE:
         TRY(expect(c.inter, h));
         TRY(pack(e, src, h, (int64_t)r * e->inter_l, 0, e->inter_l, h, L->wgu, 0, MAP_GATE));
+        TRY(pack_canon(e, src, h, (int64_t)r * e->inter_l, 0, e->inter_l, h, L->wgu_c, 0, MAP_GATE, e->kst_h));
         break;
       case LSK_W_UP:
         TRY(expect(c.inter, h));
         TRY(pack(e, src, h, (int64_t)r * e->inter_l, 0, e->inter_l, h, L->wgu, 0, MAP_UP));
+        TRY(pack_canon(e, src, h, (int64_t)r * e->inter_l, 0, e->inter_l, h, L->wgu_c, 0, MAP_UP, e->kst_h));
         break;
       case LSK_W_DOWN:
         TRY(expect(h, c.inter));
         TRY(pack(e, src, c.inter, 0, (int64_t)r * e->inter_l, h, e->inter_l, L->wd, 0, MAP_PLAIN, e->inter_l_pad));
+        TRY(pack_canon(e, src, c.inter, 0, (int64_t)r * e->inter_l, h, e->inter_l, L->wd_c, 0, MAP_PLAIN, e->kst_i));
         break;
       default:
         return fail(LSK_ERR_INVALID, "unknown weight role %d", d.role);
@@ -1178,15 +1344,24 @@ int lsk_prefill(lsk_engine* e, const int32_t* ids, int32_t n) {
   const lsk_config& c = e->cfg;
   CU(cudaEventRecord(e->ev0, e->stream));
   CU(cudaMemcpyAsync(e->d_prompt, ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-  // ids[0 .. n-2] through every layer in blocks of <= 16 rows; no LM head: the reference
-  // discards those logits too (self_speculation_generator.py:177).
-  for (int c0 = 0; c0 < n - 1; c0 += e->max_rows) {
-    const int m = (n - 1 - c0) < e->max_rows ? (n - 1 - c0) : e->max_rows;
-    CU(launch(e, embed_tokens_kernel, dim3(m), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
-              (const int*)(e->d_prompt + c0), e->hidden, c.hidden));
-    for (int l = 0; l < c.n_layers; ++l)
-      TRY(enqueue_layer(e, l, 0, m, e->d_zero, c0, e->layers[(l + 1) % c.n_layers].wqkv,
-                        (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2));
+  // ids[0 .. n-2] through every layer; no LM head: the reference discards those logits too
+  // (self_speculation_generator.py:177).  Prompts longer than one decode block go through the
+  // tcgen05 GEMMs 128 tokens per weight pass (prefill_tc.cuh), short ones through the decode
+  // kernels in blocks of <= 16 rows.
+  if (e->pf_tc && n - 1 > e->max_rows) {
+    for (int c0 = 0; c0 < n - 1; c0 += kPfTokens) {
+      const int m = (n - 1 - c0) < kPfTokens ? (n - 1 - c0) : kPfTokens;
+      TRY(enqueue_prefill_chunk(e, c0, m));
+    }
+  } else {
+    for (int c0 = 0; c0 < n - 1; c0 += e->max_rows) {
+      const int m = (n - 1 - c0) < e->max_rows ? (n - 1 - c0) : e->max_rows;
+      CU(launch(e, embed_tokens_kernel, dim3(m), dim3(256), 0, (const __nv_bfloat16*)e->embed, c.hidden,
+                (const int*)(e->d_prompt + c0), e->hidden, c.hidden));
+      for (int l = 0; l < c.n_layers; ++l)
+        TRY(enqueue_layer(e, l, 0, m, e->d_zero, c0, e->layers[(l + 1) % c.n_layers].wqkv,
+                          (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2));
+    }
   }
   set_state_kernel<<<1, 1, 0, e->stream>>>(e->state, n - 1, ids[n - 1], 0);
   CU(cudaGetLastError());
@@ -1335,6 +1510,12 @@ int lsk_debug_read(lsk_engine* e, int32_t what, int32_t layer, int64_t index, fl
     if (!src) return fail(LSK_ERR_STATE, "no sampling generation has run");
     if (n > (int64_t)kMaxRows * e->cfg.vocab) return fail(LSK_ERR_INVALID, "too many floats");
     CU(cudaMemcpy(dst, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return LSK_OK;
+  }
+  if (what == LSK_DBG_RESIDUAL) {
+    if (!e->samp_scratch) return fail(LSK_ERR_STATE, "no sampling generation has run");
+    if (n > (int64_t)e->cfg.vocab) return fail(LSK_ERR_INVALID, "too many floats");
+    CU(cudaMemcpy(dst, e->samp_scratch, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return LSK_OK;
   }
   if (what == LSK_DBG_LOGITS) {
@@ -1498,6 +1679,11 @@ int lsk_test_attn(const void* q, const void* k, const void* v, int32_t n_heads, 
       m > kMaxRows || n_splits < 1 || n_splits > 8)
     return fail(LSK_ERR_INVALID, "bad attention test shape");
   lsk_engine tmp;
+  {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&tmp.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
   CU(cudaStreamCreateWithFlags(&tmp.stream, cudaStreamNonBlocking));
   tmp.use_pdl = true;
   const int n_pages = (ctx + kPageTokens - 1) / kPageTokens;

@@ -32,7 +32,7 @@ class Engine:
     def __init__(self, arch: LlamaArch, max_ctx: int = 4096, tp_rank: int = 0, tp_size: int = 1,
                  keep_logits: bool = False, use_pdl: bool = True, use_graph: bool = True,
                  attn_splits: int = 0, device: Optional[torch.device] = None,
-                 tp_nccl: bool = False):
+                 tp_nccl: bool = False, prefill_tc: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("layerskip_b200 needs a CUDA device (B200); there is no CPU path")
         self._lib = _lib.load()
@@ -40,7 +40,23 @@ class Engine:
         self.device = torch.device(device) if device is not None else \
             torch.device("cuda", torch.cuda.current_device())
         self.tp_rank, self.tp_size = tp_rank, tp_size
+        # the tcgen05 prompt pass needs a second (canonical-layout) copy of the layer weights: on by
+        # default, dropped automatically when the two copies would not fit this GPU
+        try:
+            free_now = torch.cuda.mem_get_info(self.device)[0]
+        except Exception:  # pragma: no cover
+            free_now = None
+        if prefill_tc is None:
+            prefill_tc = os.environ.get("LSK_PREFILL_TC", "1") not in ("0",)
+            if prefill_tc and free_now is not None:
+                from .memory import plan_memory
+                plan = plan_memory(arch, max_ctx=max_ctx, tp_size=tp_size, keep_logits=keep_logits,
+                                   prefill_tc=True)
+                if plan["total"] + plan["weights_source_peak"] > free_now:
+                    prefill_tc = False
+        self.prefill_tc = bool(prefill_tc)
         flags = (_lib.LSK_FLAG_KEEP_LOGITS if keep_logits else 0) | \
+                (0 if prefill_tc else _lib.LSK_FLAG_NO_PREFILL_TC) | \
                 (0 if use_pdl else _lib.LSK_FLAG_NO_PDL) | (0 if use_graph else _lib.LSK_FLAG_NO_GRAPH) | \
                 (_lib.LSK_FLAG_TP_NCCL if tp_nccl else 0)
         cfg = _lib.lsk_config(
@@ -54,6 +70,9 @@ class Engine:
             rope_original_max_pos=arch.rope_original_max_pos)
         self.max_ctx = max_ctx
         self.keep_logits = keep_logits
+        # token rows one step can carry (engine.cu: max_rows): 16, or 8 when the 16-row kernels do
+        # not fit next to K = hidden in shared memory
+        self.max_rows = 16 if arch.hidden <= 4096 else 8
         # refuse a configuration that cannot fit BEFORE cudaMalloc fails half-way (memory.py)
         try:
             free_bytes = torch.cuda.mem_get_info(self.device)[0]
@@ -62,7 +81,8 @@ class Engine:
         if free_bytes is not None:
             from .memory import check_fits
             check_fits(arch, free_bytes, max_ctx=max_ctx, tp_size=tp_size, keep_logits=keep_logits,
-                       sampling=False, lm_head_tc=os.environ.get("LSK_LMHEAD_TC", "0") not in ("", "0"))
+                       sampling=False, lm_head_tc=os.environ.get("LSK_LMHEAD_TC", "0") not in ("", "0"),
+                       prefill_tc=self.prefill_tc)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.lsk_create(C.byref(cfg), C.byref(handle)))
@@ -242,6 +262,14 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.lsk_debug_read(self._h, what, 0, 0, buf, n))
         return torch.frombuffer(buf, dtype=torch.float32).clone().view(rows, self.arch.vocab)
+
+    def debug_residual(self) -> torch.Tensor:
+        """max(p_verify - p_draft, 0) of the last rejected draft position (unnormalised) [vocab]."""
+        n = self.arch.vocab
+        buf = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lsk_debug_read(self._h, _lib.LSK_DBG_RESIDUAL, 0, 0, buf, n))
+        return torch.frombuffer(buf, dtype=torch.float32).clone()
 
     def debug_kv_row(self, which: str, layer: int, kv_head: int, pos: int) -> torch.Tensor:
         hd = self.arch.head_dim

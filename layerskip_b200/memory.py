@@ -17,7 +17,7 @@ HBM_PER_B200 = 180e9
 
 
 def plan_memory(arch: LlamaArch, max_ctx: int = 4096, tp_size: int = 1, sampling: bool = False,
-                keep_logits: bool = False, lm_head_tc: bool = False) -> Dict[str, int]:
+                keep_logits: bool = False, lm_head_tc: bool = False, prefill_tc: bool = True) -> Dict[str, int]:
     """Bytes the engine allocates on ONE rank.  Keys: weights, embed, lm_head, kv_pool, scratch,
     total (+ weights_source_peak: the largest single tensor staged on the GPU while loading)."""
     h, L = arch.hidden, arch.layers
@@ -29,6 +29,13 @@ def plan_memory(arch: LlamaArch, max_ctx: int = 4096, tp_size: int = 1, sampling
     vocab_l_pad = (vocab_l + 15) // 16 * 16
     per_layer = 2 * ((q_l + 2 * kv_l) * h + h * q_l + 2 * inter_l * h + h * inter_l_pad) + 2 * 2 * h
     weights = L * per_layer
+    if prefill_tc and h % 64 == 0:
+        # second, canonical-layout copy of the layer weights for the tcgen05 prompt pass
+        # (128-row tiles x 64-wide k stages of 16 KiB) + its 128-token activation buffers
+        up = lambda x, m: (x + m - 1) // m     # noqa: E731
+        t_qkv, t_h, t_gu = up(q_l + 2 * kv_l, 128), up(h, 128), up(2 * inter_l, 128)
+        k_h, k_q, k_i = h // 64, up(q_l, 64), up(inter_l, 64)
+        weights += L * 16384 * (t_qkv * k_h + t_h * k_q + t_gu * k_h + t_h * k_i)
     embed = 2 * arch.vocab * h + 2 * h                       # replicated embedding + final norm
     lm_head = 2 * vocab_l_pad * h
     if lm_head_tc:
@@ -43,6 +50,8 @@ def plan_memory(arch: LlamaArch, max_ctx: int = 4096, tp_size: int = 1, sampling
         + MAX_ROWS * h * 4                     # TP partial sums
         + max_pos * (arch.head_dim // 2) * 8 + max_pos * 4 + n_pages * 4   # RoPE table, prompt ids, page table
         + 148 * MAX_ROWS * 8 + tp_size * MAX_ROWS * 8)      # arg-max candidates
+    if prefill_tc and h % 64 == 0:
+        scratch += 2 * 128 * h * 4 + 128 * q_l * 2 + 16384 * (h // 64 + (q_l + 63) // 64 + (inter_l + 63) // 64)
     if keep_logits or sampling:
         scratch += MAX_ROWS * vocab_l_pad * 4
     if sampling:

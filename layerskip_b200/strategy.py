@@ -60,16 +60,29 @@ class _EngineCache:
 
 
 def _generation_seed(cache: "_EngineCache", eng: Engine, sample: bool) -> int:
-    """The reference draws from torch's global generator; the engine's Philox streams are keyed
-    by its seed.  Under tensor parallelism every rank must draw the SAME tokens, so rank 0's seed
-    is broadcast (only when sampling: the greedy path needs no extra collective)."""
-    seed = int(torch.initial_seed()) & 0xFFFFFFFF
-    if sample and eng.tp_size > 1:
+    """The reference draws from torch's global generator, so two sampled calls differ while a run
+    under `torch.manual_seed` stays reproducible.  The engine's Philox streams are keyed by a
+    per-generation seed: draw it FROM the global generator (which advances it, like the
+    reference's own draws would).  Under tensor parallelism every rank must draw the SAME
+    tokens, so rank 0's seed is broadcast (only when sampling: greedy needs no collective)."""
+    if not sample:
+        return 0
+    seed = int(torch.randint(0, 2 ** 31 - 1, ()).item())
+    if eng.tp_size > 1:
         from .parallel_util import broadcast_bytes
         raw = broadcast_bytes(seed.to_bytes(4, "little"), 4, src=0,
                               group=cache.process_group, device=eng.device)
         seed = int.from_bytes(raw, "little")
     return seed
+
+
+def _check_num_speculations(cfg: GenerationConfig, eng) -> None:
+    """The reference accepts any positive `num_speculations`; a verify block carries at most
+    `eng.max_rows` token rows here (16; 8 when hidden > 4096).  Fail before prefill, clearly."""
+    limit = getattr(eng, "max_rows", 16) - 1
+    if cfg.num_speculations < 0 or cfg.num_speculations > limit:
+        raise ValueError(f"num_speculations={cfg.num_speculations} is outside [0, {limit}] for this model "
+                         "(the verify block holds num_speculations + 1 token rows)")
 
 
 def _check_context(eng, n_prompt: int, cfg: GenerationConfig) -> None:
@@ -107,6 +120,7 @@ class B200SelfSpeculativeGenerationStrategy(GenerationStrategy):
         cfg = generation_config
         eng = self.engines.get(model)
         _check_context(eng, len(input_ids), cfg)
+        _check_num_speculations(cfg, eng)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
                   seed=_generation_seed(self.engines, eng, cfg.sample))

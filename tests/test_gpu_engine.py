@@ -10,7 +10,7 @@ from tests import parity_util as pu
 
 pytestmark = pytest.mark.gpu
 
-ENGINE_MODELS = ("tiny_mha128", "tiny_gqa128")
+ENGINE_MODELS = ("tiny_mha128", "tiny_gqa128", "survey_mha32")   # survey_mha32 = correctness.py's config (head_dim 32)
 
 
 def _engine_cases(greedy=True):
@@ -156,7 +156,7 @@ def test_autoregressive_and_early_exit_match_reference_golden(case, strategies):
                     exit_layer=case["cfg"]["exit_layer"])
 
 
-@pytest.mark.parametrize("mname,seed", [("tiny_mha128", 1), ("tiny_gqa128", 4)])
+@pytest.mark.parametrize("mname,seed", [("tiny_mha128", 1), ("tiny_gqa128", 4), ("survey_mha32", 0)])
 def test_logits_close_to_oracle(mname, seed, strategies):
     """Engine logits vs the oracle's (and hence the reference's forward, see
     tests/golden/layer_arith.json) on a prompt: max |delta| must stay well under TAU/2."""
@@ -211,3 +211,32 @@ def test_unsupported_inputs_fail_loudly(strategies):
     with pytest.raises(NotImplementedError):
         spec.generate_token_ids(model, case["prompt"], case["eos"], _gen_cfg(case),
                                 logits_processors=[lambda i, s: s])
+
+
+def test_tcgen05_prefill_matches_the_decode_kernel_prefill(monkeypatch):
+    """lsk_prefill through the 128-token tcgen05 GEMMs (csrc/prefill_tc.cuh) vs the same prompt
+    16 rows at a time through the decode kernels: same K/V rows up to bf16 rounding of different
+    accumulation orders, next-step logits within the usual engine-vs-oracle tolerance, same token."""
+    from layerskip_b200.engine import Engine
+    from layerskip_b200.weights import LlamaArch
+    case = next(c for c in gu.spec_cases() if c["name"] == "gqa128_a0.05_long")   # 70-token prompt
+    dims, model, w = _model_for(case)
+    arch = LlamaArch.from_hf_config(model.config)
+    g = torch.Generator().manual_seed(7)
+    prompt = torch.randint(3, dims.vocab - 1, (300,), generator=g).tolist()      # 3 chunks: 128 + 128 + 43
+    out = {}
+    for tc in (True, False):
+        eng = Engine(arch, max_ctx=512, keep_logits=True, prefill_tc=tc)
+        eng.load_model(model)
+        eng.begin(exit_layer=-1, max_steps=4, eos_token_ids=[dims.vocab - 1])
+        eng.prefill(prompt)
+        rows = [eng.debug_kv_row(which, layer, 0, pos) for which in "kv" for layer in (0, dims.layers - 1)
+                for pos in (0, 127, 128, 298)]
+        tok = eng.ar_step()
+        out[tc] = (torch.stack(rows), eng.debug_logits(1)[0], tok)
+        eng.close()
+    torch.testing.assert_close(out[True][0], out[False][0], rtol=2e-2, atol=2e-2)
+    assert float((out[True][1] - out[False][1]).abs().max()) < pu.TAU / 2
+    want = orc.teacher_forced_logits(w, prompt, [0])[0]
+    assert float((out[True][1] - want).abs().max()) < pu.TAU / 2
+    assert out[True][2] == out[False][2] or float(want.max() - want[out[True][2]]) < pu.TAU

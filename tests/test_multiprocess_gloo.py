@@ -60,7 +60,8 @@ def _seed_worker(rank, world, port, q):
         torch.manual_seed(1000 + rank)                      # ranks disagree, like unseeded processes
         eng = type("E", (), dict(tp_size=world, device=None))()
         cache = _EngineCache(tp_size=world)
-        q.put((rank, _generation_seed(cache, eng, True), _generation_seed(cache, eng, False)))
+        a, b = _generation_seed(cache, eng, True), _generation_seed(cache, eng, True)
+        q.put((rank, a, _generation_seed(cache, eng, False), b))
     finally:
         dist.destroy_process_group()
 
@@ -77,5 +78,9 @@ def test_sampling_seed_is_rank_zeros_on_every_tp_rank():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0][1] == res[1][1] == 1000                  # sampling: rank 0's seed everywhere
-    assert (res[0][2], res[1][2]) == (1000, 1001)          # greedy: no collective, local seed
+    import torch
+    torch.manual_seed(1000)
+    want = [int(torch.randint(0, 2 ** 31 - 1, ()).item()) for _ in range(2)]
+    assert res[0][1] == res[1][1] == want[0]               # sampling: rank 0's draw on every rank
+    assert res[0][3] == res[1][3] == want[1] != want[0]    # the next call gets a fresh seed
+    assert (res[0][2], res[1][2]) == (0, 0)                # greedy: no collective, no RNG consumed

@@ -546,7 +546,8 @@ def run_b200_arm(args):
     if tp > 1 and (arch.heads % tp or arch.kv_heads % tp):
         raise SystemExit(f"{args.arch}: {arch.kv_heads} kv heads do not divide by {tp} ranks")
     model = SyntheticLlama(arch, seed=0, alpha=args.alpha, damp_from=args.exit_layer, device="cuda")
-    max_ctx = ((args.prompt_len + args.max_steps + 64 + 63) // 64) * 64
+    # KV pool: the workload's context, and room for the 1024-id prefill measurement of the extras
+    max_ctx = max(((args.prompt_len + args.max_steps + 64 + 63) // 64) * 64, 1152)
     eos = [arch.vocab - 1]
     gcfg = GenerationConfig(max_steps=args.max_steps, exit_layer=args.exit_layer,
                             num_speculations=args.num_speculations, sample=False,

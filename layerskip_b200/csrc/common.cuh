@@ -117,14 +117,18 @@ __host__ __device__ __forceinline__ size_t kv_elem_offset(int hd, int page, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// Canonical K-major operand layout of the tcgen05 kernels (prefill_tc.cuh, lmhead_tc.cuh):
-// stages of 128 rows x 64 k (16 KiB) made of 8-row x 16-byte core matrices,
-// core(row group i, k chunk j) at (i*8 + j)*128 B.  Byte offset of element (row < 128, k):
+// K-major SWIZZLE_128B operand layout of the tcgen05 prefill GEMM (prefill_tc.cuh): stages of
+// 128 rows x 64 k (16 KiB); a row's 64 k (128 bytes) are contiguous, rows 128 bytes apart, and
+// inside every 8-row / 1 KiB atom the 16-byte chunks are XOR-swizzled with the row index — the
+// layout a TMA tensor copy with CU_TENSOR_MAP_SWIZZLE_128B would produce, written here directly
+// by the producing kernels so that plain 1-D bulk copies can move it.  (The SWIZZLE_NONE
+// core-matrix layout of round 1 ran the tensor pipe at ~1/4 rate: bank conflicts on operand fetch.)
+// Byte offset of element (row < 128, k):
 // ---------------------------------------------------------------------------------------
 constexpr int kCanonStageBytes = 128 * 64 * 2;
 __host__ __device__ __forceinline__ size_t canon_offset(int row, int k) {
-  const int s = k >> 6, j = (k >> 3) & 7, i = row >> 3, r = row & 7;
-  return (size_t)s * kCanonStageBytes + (size_t)(i * 8 + j) * 128 + r * 16 + (k & 7) * 2;
+  const int s = k >> 6, c = (k >> 3) & 7;
+  return (size_t)s * kCanonStageBytes + (size_t)row * 128 + ((c ^ (row & 7)) << 4) + (k & 7) * 2;
 }
 
 // Device-resident generation state (one per engine).  `tok[0]` is the pending input token,

@@ -115,6 +115,7 @@ struct lsk_engine {
   int pf_t_qkv = 0, pf_t_h = 0, pf_t_gu = 0;     // 128-row tiles of qkv / hidden / gate-up outputs
   float* hidden_p = nullptr;             // [128][hidden] fp32 residual rows of a prompt chunk
   float* tp_buf_p = nullptr;             // [128][hidden] fp32 row-parallel partial sums (TP)
+  float* part_p = nullptr;               // [4 k-splits][128][hidden] fp32 partial tiles of the O / down GEMMs
   __nv_bfloat16* q_p = nullptr;          // [128][q_rows]
   unsigned char* xn_c = nullptr;         // canonical activations: RMS-normed rows   [kst_h][16 KiB]
   unsigned char* attn_c = nullptr;       //                        attention output   [kst_q][16 KiB]
@@ -542,7 +543,8 @@ static int enqueue_layer(lsk_engine* e, int li, int row0, int M, const int* base
 template <int EPI>
 static int launch_prefill_gemm(lsk_engine* e, PrefillGemmArgs& a) {
   a.n_stages = e->pf_stages;
-  const int grid = a.n_tiles < e->sm_count ? a.n_tiles : e->sm_count;
+  const int items = a.n_tiles * (EPI == PF_EPI_STORE && a.k_splits > 1 ? a.k_splits : 1);
+  const int grid = items < e->sm_count ? items : e->sm_count;
   CU(launch(e, prefill_gemm_tc_kernel<EPI>, dim3(grid), dim3(kTcThreads), prefill_tc_smem_bytes(a.n_stages), a));
   return LSK_OK;
 }
@@ -556,28 +558,50 @@ static int enqueue_prefill_chunk(lsk_engine* e, int c0, int m) {
   // rows of one attention launch: as many as fit its shared-memory plan (multiple of 16)
   int m_attn = 16;
   for (int cand = kPfTokens; cand >= 16; cand -= 16)
-    if (attn_smem_plan(c.head_dim, e->group, cand).total <= (size_t)kSmemMax) { m_attn = cand; break; }
+    if (attn_smem_plan(c.head_dim, e->group, cand, 2).total <= (size_t)kSmemMax) { m_attn = cand; break; }
+  // row-parallel GEMMs (O / down): hidden / 128 feature tiles are too few to keep the SMs streaming
+  // -> split K; the partial tiles are summed (fixed order) by the next rms_canon_kernel
+  const int ks_o = std::max(1, std::min(std::min(4, e->kst_q), e->sm_count / e->pf_t_h));
+  const int ks_d = std::max(1, std::min(std::min(4, e->kst_i), e->sm_count / e->pf_t_h));
+  const size_t part_stride = (size_t)kPfTokens * c.hidden;
+  // pending row-parallel partials that the next norm kernel has to add to the residual rows
+  const float* pend = nullptr;
+  int n_pend = 0;
+  auto after_row_parallel = [&](int n_splits) -> int {
+    if (!tp) { pend = e->part_p; n_pend = n_splits; return LSK_OK; }
+    e->cur_class = CLS_COMM;
+    CU(launch(e, reduce_partials_kernel, dim3(m), dim3(256), 0, (const float*)e->part_p, n_splits, part_stride,
+              c.hidden, c.hidden, e->tp_buf_p));
+    e->launches += 1;
+    e->capture_launches += 1;
+    NC(ncclAllReduce(e->tp_buf_p, e->tp_buf_p, (size_t)m * c.hidden, ncclFloat, ncclSum, e->comm, e->stream));
+    pend = e->tp_buf_p; n_pend = 1;
+    return LSK_OK;
+  };
   for (int li = 0; li < c.n_layers; ++li) {
     LayerWeights& L = e->layers[li];
     __nv_bfloat16* kp = e->kpool + (size_t)li * e->pool_layer_elems;
     __nv_bfloat16* vp = e->vpool + (size_t)li * e->pool_layer_elems;
     e->cur_class = CLS_QKV;
-    CU(launch(e, rms_canon_kernel, dim3(m), dim3(256), 0, (const float*)e->hidden_p, c.hidden,
+    CU(launch(e, rms_canon_kernel, dim3(m), dim3(256), 0, e->hidden_p, c.hidden, pend, n_pend, part_stride,
               (const __nv_bfloat16*)L.ln1, c.rms_eps, c.hidden, e->xn_c));
     {
       PrefillGemmArgs a{};
       a.W = L.wqkv_c; a.X = e->xn_c; a.n_tiles = e->pf_t_qkv; a.n_rows = e->q_rows + 2 * e->kv_rows;
-      a.n_kst = e->kst_h; a.M = m;
+      a.n_kst = e->kst_h; a.M = m; a.k_splits = 1;
       a.q_out = e->q_p; a.q_ld = e->q_rows; a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
       a.pos0 = c0; a.rope = e->rope; a.head_dim = c.head_dim;
       a.q_rows = e->q_rows; a.kv_rows = e->kv_rows; a.n_kv_heads = e->kv_heads_l;
       TRY(launch_prefill_gemm<PF_EPI_QKV>(e, a));
     }
+    // the prompt pass has no LM head (the reference discards those logits): once the last layer's
+    // K/V rows are written nothing downstream is needed
+    if (li + 1 == c.n_layers) break;
     e->cur_class = CLS_ATTN;
     for (int r0 = 0; r0 < m; r0 += m_attn) {
       AttnArgs a{};
       a.q = e->q_p + (size_t)r0 * e->q_rows; a.q_ld = e->q_rows;
-      // canonical rows are addressed by token index inside the 128-row operand: shift by r0 rows
+      // operand rows are addressed by token index inside the 128-row stage: shift by r0 rows
       a.out = reinterpret_cast<__nv_bfloat16*>(e->attn_c + canon_offset(r0, 0)); a.out_canon = 1;
       a.kpool = kp; a.vpool = vp; a.page_table = e->page_table;
       a.base_len = e->d_zero; a.pos_off = c0 + r0; a.M = (m - r0) < m_attn ? (m - r0) : m_attn;
@@ -589,26 +613,26 @@ static int enqueue_prefill_chunk(lsk_engine* e, int c0, int m) {
     {
       PrefillGemmArgs a{};
       a.W = L.wo_c; a.X = e->attn_c; a.n_tiles = e->pf_t_h; a.n_rows = c.hidden; a.n_kst = e->kst_q; a.M = m;
-      a.out_f32 = tp ? e->tp_buf_p : e->hidden_p; a.out_ld = c.hidden;
-      if (!tp) TRY(launch_prefill_gemm<PF_EPI_RESID>(e, a));
-      else { TRY(launch_prefill_gemm<PF_EPI_STORE>(e, a)); TRY(emit_allreduce_resid_nccl(e, e->tp_buf_p, e->hidden_p, m)); }
+      a.k_splits = ks_o; a.out_f32 = e->part_p; a.out_ld = c.hidden;
+      TRY(launch_prefill_gemm<PF_EPI_STORE>(e, a));
+      TRY(after_row_parallel(ks_o));
     }
     e->cur_class = CLS_GATEUP;
-    CU(launch(e, rms_canon_kernel, dim3(m), dim3(256), 0, (const float*)e->hidden_p, c.hidden,
+    CU(launch(e, rms_canon_kernel, dim3(m), dim3(256), 0, e->hidden_p, c.hidden, pend, n_pend, part_stride,
               (const __nv_bfloat16*)L.ln2, c.rms_eps, c.hidden, e->xn_c));
     {
       PrefillGemmArgs a{};
       a.W = L.wgu_c; a.X = e->xn_c; a.n_tiles = e->pf_t_gu; a.n_rows = 2 * e->inter_l; a.n_kst = e->kst_h; a.M = m;
-      a.act_canon = e->act_c;
+      a.k_splits = 1; a.act_canon = e->act_c;
       TRY(launch_prefill_gemm<PF_EPI_SILU>(e, a));
     }
     e->cur_class = CLS_DOWN;
     {
       PrefillGemmArgs a{};
       a.W = L.wd_c; a.X = e->act_c; a.n_tiles = e->pf_t_h; a.n_rows = c.hidden; a.n_kst = e->kst_i; a.M = m;
-      a.out_f32 = tp ? e->tp_buf_p : e->hidden_p; a.out_ld = c.hidden;
-      if (!tp) TRY(launch_prefill_gemm<PF_EPI_RESID>(e, a));
-      else { TRY(launch_prefill_gemm<PF_EPI_STORE>(e, a)); TRY(emit_allreduce_resid_nccl(e, e->tp_buf_p, e->hidden_p, m)); }
+      a.k_splits = ks_d; a.out_f32 = e->part_p; a.out_ld = c.hidden;
+      TRY(launch_prefill_gemm<PF_EPI_STORE>(e, a));
+      TRY(after_row_parallel(ks_d));
     }
   }
   return LSK_OK;
@@ -979,12 +1003,12 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   if (e->pf_tc) {
     TRY(alloc((void**)&e->hidden_p, (size_t)kPfTokens * h * 4));
     TRY(alloc((void**)&e->tp_buf_p, (size_t)kPfTokens * h * 4));
+    TRY(alloc((void**)&e->part_p, (size_t)4 * kPfTokens * h * 4));
     TRY(alloc((void**)&e->q_p, (size_t)kPfTokens * e->q_rows * 2));
     TRY(alloc((void**)&e->xn_c, (size_t)e->kst_h * kCanonStageBytes));
     TRY(alloc((void**)&e->attn_c, (size_t)e->kst_q * kCanonStageBytes));
     TRY(alloc((void**)&e->act_c, (size_t)e->kst_i * kCanonStageBytes));
     CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CU(cudaFuncSetAttribute(prefill_gemm_tc_kernel<PF_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   }
@@ -1068,7 +1092,7 @@ void lsk_destroy(lsk_engine* e) {
     cudaFree(L.wqkv_c); cudaFree(L.wo_c); cudaFree(L.wgu_c); cudaFree(L.wd_c);
   }
   {
-    void* pf[] = {e->hidden_p, e->tp_buf_p, e->q_p, e->xn_c, e->attn_c, e->act_c};
+    void* pf[] = {e->hidden_p, e->tp_buf_p, e->part_p, e->q_p, e->xn_c, e->attn_c, e->act_c};
     for (void* p : pf) if (p) cudaFree(p);
   }
   void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->lm_head_tc, e->kpool, e->vpool, e->page_table, e->rope,

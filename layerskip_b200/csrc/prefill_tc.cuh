@@ -20,13 +20,18 @@
 // allocator + single-lane tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld 32x32b: warp w
 // owns TMEM lanes 32 (w % 4) .. + 31 = 32 output features, all 128 token columns).
 //
-// Operand layouts (canonical K-major, 8 rows x 16 B core matrices):
-//   stage (128 rows x 64 k) = 16 KiB: core(row group i = 0..15, k chunk j = 0..7) at (i*8 + j)*128 B
-//   -> descriptor LBO = 128 B (next k chunk), SBO = 1024 B (next 8 rows); one tcgen05.mma eats
-//   K = 16 (two chunks): 4 MMAs per stage, descriptors advance by 256 B.
-//   Weights: [tile][k stage][16 KiB], packed once by pack_canonical_kernel with the SAME row
-//   permutations as the decode layout (rotary pairs / gate-up pairs sit 8 rows apart).
-//   Activations: [k stage][16 KiB] with rows = tokens, written by the producing kernel.
+// Operand layouts (common.cuh: canon_offset): K-major SWIZZLE_128B — stage (128 rows x 64 k) =
+//   16 KiB, row r at r*128 B, 16-byte chunk c of a row stored at c ^ (r & 7).  Descriptor: layout
+//   type 2 (SWIZZLE_128B), SBO = 1024 B (next 8-row atom), LBO unused (1); one tcgen05.mma eats
+//   K = 16 = 32 bytes of a row: 4 MMAs per stage, start address advancing by 32 B.
+//   Weights: [tile][k stage][16 KiB], packed once with the SAME row permutations as the decode
+//   layout (rotary pairs / gate-up pairs sit 8 rows apart).  Activations: [k stage][16 KiB] with
+//   rows = tokens, written in this layout by the producing kernel.
+//
+// Grid: one CTA per work item wave; a work item = (feature tile, k split).  Row-parallel GEMMs with
+// few feature tiles (O / down projections: hidden / 128 = 32 tiles at 7B) split K so that ~all SMs
+// stream weights; their fp32 partial tiles go to per-split buffers that the NEXT kernel
+// (rms_canon_kernel: residual add + RMSNorm) sums in fixed order — deterministic, no atomics.
 #pragma once
 #include "lmhead_tc.cuh"
 #include "misc_kernels.cuh"
@@ -38,7 +43,7 @@ constexpr int kPfStageBytes = 2 * kTcStageBytes;   // A stage + B stage
 constexpr int kPfMaxStages = 6;
 constexpr int kPfTmemCols = 256;               // 2 accumulators x 128 token columns
 
-enum { PF_EPI_QKV = 0, PF_EPI_RESID = 1, PF_EPI_STORE = 2, PF_EPI_SILU = 3 };
+enum { PF_EPI_QKV = 0, PF_EPI_STORE = 2, PF_EPI_SILU = 3 };
 
 struct PrefillGemmArgs {
   const unsigned char* W;      // canonical weights [n_tiles][n_kst][16 KiB]
@@ -48,7 +53,8 @@ struct PrefillGemmArgs {
   int n_kst;                   // K / 64 (K padded to 64)
   int M;                       // valid token rows (<= 128)
   int n_stages;
-  // RESID (+=) / STORE (=): out_f32[tok][f]
+  int k_splits;                // work items per tile (STORE only; 1 otherwise)
+  // STORE: out_f32[k split][tok][f]  (split stride = kPfTokens * out_ld floats)
   float* out_f32;
   int out_ld;
   // SILU: act canonical [inter_pad / 64][16 KiB]; packed rows (16-row groups: 8 gate, 8 up)
@@ -67,6 +73,13 @@ struct PrefillGemmArgs {
 
 __host__ __device__ inline size_t prefill_tc_smem_bytes(int n_stages) {
   return (size_t)kTcHeaderBytes + (size_t)n_stages * kPfStageBytes;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor: start address,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B, version 1, layout type 2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
 }
 
 __device__ __forceinline__ void tmem_alloc_cols(uint32_t* smem_dst, uint32_t cols) {      // whole warp
@@ -107,20 +120,26 @@ __global__ void pack_canonical_rows_kernel(const __nv_bfloat16* __restrict__ src
   }
 }
 
-// RMSNorm of the fp32 residual rows -> canonical bf16 activations (the rounding point of a bf16
-// HF model, modeling_llama.py:52-70).  One CTA per token row.
+// x[tok] += sum of the `n_part` partial rows (fixed order; the split-K / tensor-parallel partials of
+// the previous row-parallel GEMM), written back, then RMSNorm -> bf16 activations in the operand
+// layout (the rounding point of a bf16 HF model, modeling_llama.py:52-70).  One CTA per token row.
 __global__ void __launch_bounds__(256)
-rms_canon_kernel(const float* __restrict__ x, int x_ld, const __nv_bfloat16* __restrict__ norm_w, float eps,
-                 int K, unsigned char* __restrict__ dst) {
+rms_canon_kernel(float* __restrict__ x, int x_ld, const float* __restrict__ part, int n_part, size_t part_stride,
+                 const __nv_bfloat16* __restrict__ norm_w, float eps, int K, unsigned char* __restrict__ dst) {
   __shared__ float s_part[8];
   pdl_launch_dependents();
   pdl_wait();
   const int tok = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * x_ld);
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)tok * x_ld);
   const int nvec = K >> 2;
   float ss = 0.f;
   for (int i = tid; i < nvec; i += 256) {
-    const float4 v = xr[i];
+    float4 v = xr[i];
+    for (int p = 0; p < n_part; ++p) {
+      const float4 d = *reinterpret_cast<const float4*>(part + (size_t)p * part_stride + (size_t)tok * x_ld + i * 4);
+      v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+    }
+    if (n_part > 0) xr[i] = v;
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   ss = warp_sum(ss);
@@ -130,13 +149,31 @@ rms_canon_kernel(const float* __restrict__ x, int x_ld, const __nv_bfloat16* __r
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += s_part[w];
   const float rstd = rsqrtf(tot / (float)K + eps);
+  if (dst == nullptr) return;                       // residual update only
   for (int i = tid; i < nvec; i += 256) {
-    const float4 v = xr[i];
+    const float4 v = xr[i];                         // own writes: same thread, same address
     const uint2 wv = *reinterpret_cast<const uint2*>(norm_w + i * 4);
     uint2 o;
     o.x = pack_bf16x2(bf16_lo(wv.x) * (v.x * rstd), bf16_hi(wv.x) * (v.y * rstd));
     o.y = pack_bf16x2(bf16_lo(wv.y) * (v.z * rstd), bf16_hi(wv.y) * (v.w * rstd));
     *reinterpret_cast<uint2*>(dst + canon_offset(tok, i * 4)) = o;
+  }
+}
+
+// tensor parallel: out[tok] = sum of the local split-K partials (fixed order), all-reduced afterwards
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int n_part, size_t part_stride, int ld, int K,
+                       float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tok = blockIdx.x;
+  for (int i = threadIdx.x; i < (K >> 2); i += 256) {
+    float4 v = *reinterpret_cast<const float4*>(part + (size_t)tok * ld + i * 4);
+    for (int p = 1; p < n_part; ++p) {
+      const float4 d = *reinterpret_cast<const float4*>(part + (size_t)p * part_stride + (size_t)tok * ld + i * 4);
+      v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)tok * ld + i * 4) = v;
   }
 }
 
@@ -152,6 +189,8 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
   unsigned char* ring = smem + kTcHeaderBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = a.n_stages;
+  const int KS = (EPI == PF_EPI_STORE && a.k_splits > 1) ? a.k_splits : 1;
+  const int n_items = a.n_tiles * KS;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -171,8 +210,10 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
     if (lane == 0) {
       // ============================================================ TMA PRODUCER
       uint32_t q = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
-        for (int s = 0; s < a.n_kst; ++s, ++q) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / KS, ks = item - tile * KS;
+        const int s_lo = (int)((long long)a.n_kst * ks / KS), s_hi = (int)((long long)a.n_kst * (ks + 1) / KS);
+        for (int s = s_lo; s < s_hi; ++s, ++q) {
           const int st = q % NS;
           mbar_wait_bounded(&empty_bar[st], ((q / NS) & 1) ^ 1);
           mbar_arrive_expect_tx(&full_bar[st], kPfStageBytes);
@@ -180,6 +221,7 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
           tma_bulk_g2s(dst, a.W + ((size_t)tile * a.n_kst + s) * kTcStageBytes, kTcStageBytes, &full_bar[st]);
           tma_bulk_g2s(dst + kTcStageBytes, a.X + (size_t)s * kTcStageBytes, kTcStageBytes, &full_bar[st]);
         }
+      }
     }
   } else if (warp == 1) {
     // ============================================================== MMA ISSUER (one lane)
@@ -187,12 +229,15 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTcTileRows, kPfTokens);
       uint32_t q = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int tile = item / KS, ks = item - tile * KS;
+        const int s_lo = (int)((long long)a.n_kst * ks / KS), s_hi = (int)((long long)a.n_kst * (ks + 1) / KS);
+        (void)tile;
         const int buf = it & 1;
         mbar_wait_bounded(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)buf * kPfTokens;
-        for (int s = 0; s < a.n_kst; ++s, ++q) {
+        for (int s = s_lo; s < s_hi; ++s, ++q) {
           const int st = q % NS;
           mbar_wait_bounded(&full_bar[st], (q / NS) & 1);
           tc_fence_after();
@@ -200,9 +245,9 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
           const uint32_t b_addr = a_addr + kTcStageBytes;
 #pragma unroll
           for (int k = 0; k < kTcStageK / 16; ++k) {
-            const uint64_t da = umma_desc(a_addr + k * 256, 128, 1024);
-            const uint64_t db = umma_desc(b_addr + k * 256, 128, 1024);
-            umma_bf16_ss(d_addr, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32);
+            umma_bf16_ss(d_addr, da, db, idesc, (s > s_lo || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[st]);               // frees the ring slot once these MMAs have read it
         }
@@ -213,7 +258,8 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
     // ================================================================ EPILOGUE (4 warps x 32 features)
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int tile = item / KS, ks = item - tile * KS;
       const int buf = it & 1;
       mbar_wait_bounded(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -225,15 +271,12 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
         if (c0 >= a.M) break;                        // warp-uniform: no token rows beyond M
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kPfTokens + c0), v);
-        if (EPI == PF_EPI_RESID || EPI == PF_EPI_STORE) {
+        if (EPI == PF_EPI_STORE) {
+          float* outp = a.out_f32 + (size_t)ks * kPfTokens * a.out_ld + prow;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int tok = c0 + j;
-            if (tok < a.M && valid) {
-              float* p = a.out_f32 + (size_t)tok * a.out_ld + prow;
-              const float val = __uint_as_float(v[j]);
-              *p = (EPI == PF_EPI_RESID) ? *p + val : val;
-            }
+            if (tok < a.M && valid) outp[(size_t)tok * a.out_ld] = __uint_as_float(v[j]);
           }
         } else if (EPI == PF_EPI_SILU) {
           // 16-row groups: rows 0..7 gate, rows 8..15 up of the same 8 features (MAP_GATE / MAP_UP)
@@ -249,7 +292,28 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
             }
           }
         } else {  // PF_EPI_QKV
+          // everything that depends only on the output row is computed once per thread; the RoPE
+          // factors of the 32 tokens are fetched up front (independent loads, one round trip)
           const int HD = a.head_dim, half = HD >> 1;
+          const bool is_q = prow < a.q_rows, is_k = !is_q && prow < a.q_rows + a.kv_rows;
+          const int rel = is_q ? prow : (is_k ? prow - a.q_rows : prow - a.q_rows - a.kv_rows);
+          const int head = rel / HD, inhead = rel - head * HD;
+          const bool upper = r16 >= 8;                              // upper row of a rotary pair
+          const int d = (inhead >> 4) * 8 + (r16 & 7);              // pair index (q / k rows)
+          const int dd = (is_q || is_k) ? (upper ? d + half : d) : inhead;
+          const float2* __restrict__ rope = a.rope;
+          float2 cs[32];
+          if (is_q || is_k) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int tok = min(c0 + j, a.M - 1);
+              cs[j] = __ldg(rope + (size_t)(a.pos0 + tok) * half + d);
+            }
+          }
+          const int page_lo = a.page_table[(a.pos0 + c0) >> 6];
+          const int page_hi = a.page_table[(a.pos0 + min(c0 + 31, a.M - 1)) >> 6];
+          __nv_bfloat16* __restrict__ qo = a.q_out + head * HD + dd;
+          __nv_bfloat16* __restrict__ pool = is_k ? a.kpool : a.vpool;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float mine = __uint_as_float(v[j]);
@@ -257,26 +321,16 @@ prefill_gemm_tc_kernel(const PrefillGemmArgs a) {
             const int tok = c0 + j;
             if (tok >= a.M || !valid) continue;
             const int pos = a.pos0 + tok;
-            if (prow < a.q_rows + a.kv_rows) {           // q or k: rotary pair (d, d + HD/2) = rows (r, r + 8)
-              const bool is_q = prow < a.q_rows;
-              const int rel = is_q ? prow : prow - a.q_rows;
-              const int head = rel / HD, tt = (rel % HD) >> 4;
-              const int d = tt * 8 + (r16 & 7);
-              const float2 cs = a.rope[(size_t)pos * half + d];
-              // lower row of the pair holds x[d] (lo), upper row x[d + half] (hi)
-              const float outv = (r16 < 8) ? mine * cs.x - other * cs.y : mine * cs.x + other * cs.y;
-              const int dd = (r16 < 8) ? d : d + half;
-              if (is_q) {
-                a.q_out[(size_t)tok * a.q_ld + head * HD + dd] = __float2bfloat16_rn(outv);
-              } else {
-                const int page = a.page_table[pos >> 6];
-                a.kpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, dd)] = __float2bfloat16_rn(outv);
-              }
-            } else {                                     // v: natural order
-              const int rel = prow - a.q_rows - a.kv_rows;
-              const int head = rel / HD, d0 = rel % HD;
-              const int page = a.page_table[pos >> 6];
-              a.vpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d0)] = __float2bfloat16_rn(mine);
+            // lower row of the pair holds x[d] (lo), upper row x[d + half] (hi):
+            //   out_lo = lo cos - hi sin,  out_hi = hi cos + lo sin   (rotate_half, modeling_llama.py:138-168)
+            float outv = mine;
+            if (is_q || is_k) outv = upper ? mine * cs[j].x + other * cs[j].y : mine * cs[j].x - other * cs[j].y;
+            const __nv_bfloat16 ob = __float2bfloat16_rn(outv);
+            if (is_q) {
+              qo[(size_t)tok * a.q_ld] = ob;
+            } else {
+              const int page = ((pos >> 6) == ((a.pos0 + c0) >> 6)) ? page_lo : page_hi;
+              pool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, dd)] = ob;
             }
           }
         }

@@ -51,7 +51,7 @@ def plan_memory(arch: LlamaArch, max_ctx: int = 4096, tp_size: int = 1, sampling
         + max_pos * (arch.head_dim // 2) * 8 + max_pos * 4 + n_pages * 4   # RoPE table, prompt ids, page table
         + 148 * MAX_ROWS * 8 + tp_size * MAX_ROWS * 8)      # arg-max candidates
     if prefill_tc and h % 64 == 0:
-        scratch += 2 * 128 * h * 4 + 128 * q_l * 2 + 16384 * (h // 64 + (q_l + 63) // 64 + (inter_l + 63) // 64)
+        scratch += 6 * 128 * h * 4 + 128 * q_l * 2 + 16384 * (h // 64 + (q_l + 63) // 64 + (inter_l + 63) // 64)
     if keep_logits or sampling:
         scratch += MAX_ROWS * vocab_l_pad * 4
     if sampling:

@@ -891,14 +891,15 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   e->use_pdl = !(c.flags & LSK_FLAG_NO_PDL);
   e->use_graph = !(c.flags & LSK_FLAG_NO_GRAPH);
   e->keep_logits = (c.flags & LSK_FLAG_KEEP_LOGITS) != 0;
-  // tensor-parallel collectives: one-shot kernels over peer-mapped HBM by default
-  // (LSK_TP_ONESHOT: 0 = NCCL, 1 = LL push + reduce kernel, 2 = LL push fused into the GEMM epilogue,
-  //  3 = fence + flag protocol); LSK_FLAG_TP_NCCL forces NCCL from the API
+  // tensor-parallel collectives: one-shot kernels over peer-mapped HBM.  Default 2 = the
+  // row-parallel GEMM pushes its tiles to every rank from its own epilogue as LL lines (measured
+  // 7B TP=2: 173 tok/s; 1 = separate LL push + reduce kernel 169; 3 = fence + flag protocol 129;
+  // 0 = NCCL 134 — profiles/r2_tp2_modes.md).  LSK_FLAG_TP_NCCL forces NCCL from the API.
   {
     const char* env = getenv("LSK_TP_ONESHOT");
-    const int mode = env ? atoi(env) : ((c.flags & LSK_FLAG_TP_NCCL) ? 0 : 1);
+    const int mode = env ? atoi(env) : ((c.flags & LSK_FLAG_TP_NCCL) ? 0 : 2);
     e->want_peer = c.tp_size > 1 && mode != 0;
-    e->peer_mode = (mode >= 1 && mode <= 3) ? mode : 1;
+    e->peer_mode = (mode >= 1 && mode <= 3) ? mode : 2;
   }
   if (const char* env = getenv("LSK_ABLATE")) {
     // diagnostics only: the named kernel classes are not launched (results are garbage, the
@@ -929,8 +930,9 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   // split-KV factor: a constant of the engine (results are batch-invariant only for a fixed
   // partition).  Measured (profiles/r2_attention_sweep.md): the kernel is bound by per-SM load
   // bandwidth and barrier latency, so the best grid is ONE CTA per SM on as many SMs as possible —
-  // splits = floor(SMs / kv heads), at most the portable cluster size 8 (7B: 32 heads x 4 splits).
-  e->n_splits = c.attn_splits > 0 ? c.attn_splits : std::max(1, std::min(8, e->sm_count / std::max(1, e->kv_heads_l)));
+  // splits = floor(SMs / kv heads), at most 4 (7B: 32 heads x 4 splits; an 8-CTA cluster's barrier
+  // and 8-way merge cost more than the extra SMs bring: 16 heads x 8 splits ran 23 us against 15).
+  e->n_splits = c.attn_splits > 0 ? c.attn_splits : std::max(1, std::min(4, e->sm_count / std::max(1, e->kv_heads_l)));
   if (const char* env = getenv("LSK_ATTN_SPLITS")) e->n_splits = atoi(env);   // clamped to [1, 8] below
   if (const char* env = getenv("LSK_ATTN_STAGES")) e->attn_stages = atoi(env);
   if (e->attn_stages < 2) e->attn_stages = 2;

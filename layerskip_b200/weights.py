@@ -122,6 +122,8 @@ ARCHS: Dict[str, LlamaArch] = {
     "tiny-mha": LlamaArch(512, 256, 704, 4, 2, 2, 128, 1e-5, 10000.0),
     "tiny-gqa": LlamaArch(640, 512, 1408, 6, 4, 2, 128, 1e-5, 10000.0),
     "small-1b": LlamaArch(32000, 2048, 5632, 8, 16, 16, 128, 1e-5, 10000.0),
+    # two layers of Llama-2-7B width: numerics probes without 32 layers of perturbation growth
+    "llama2-7b-l2": LlamaArch(32000, 4096, 11008, 2, 32, 32, 128, 1e-5, 10000.0),
     # per-rank shapes of Llama-2-70B at TP=8 when run at TP=4 (8 layers): hidden 8192, 8 q heads and
     # 1 kv head per rank, 3584 FFN columns per rank — multi-GPU smoke test of config 5 on 4 GPUs
     "mini70b-tp4": LlamaArch(32000, 8192, 14336, 8, 32, 4, 128, 1e-5, 10000.0),

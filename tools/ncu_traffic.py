@@ -23,7 +23,7 @@ OUT = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
 
 WANT = {
     "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
-    "gpu__time_duration.sum": "duration", "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
+    "gpu__time_duration.sum": "duration", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed": "dram_pct",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
     "sm__inst_executed_pipe_tensor.sum": "tensor_inst",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
@@ -35,7 +35,7 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3,
 
 
 def classify(name: str, grid: float) -> str:
-    m = re.search(r"gemm_skinny_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", name)
+    m = re.search(r"gemm_skinny_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+)>", name)
     if m:
         pro, epi = int(m.group(2)), int(m.group(3))
         return {(0, 0): "qkv", (1, 1): "o_or_down", (1, 2): "o_or_down_tp", (0, 3): "gate_up",
@@ -52,18 +52,22 @@ def main():
     path, key = sys.argv[1], sys.argv[2]
     rows = {}
     with open(path, newline="") as f:
-        rd = csv.DictReader(l for l in f if not l.startswith("=="))
-        for r in rd:
-            metric = r.get("Metric Name")
-            if metric not in WANT:
+        table = [r for r in csv.reader(l for l in f if not l.startswith("=="))]
+    header, units = table[0], table[1]          # `--page raw --csv`: one column per metric, a units row
+    col = {h: i for i, h in enumerate(header)}
+    for r in table[2:]:
+        ent = {"name": r[col["Kernel Name"]]}
+        g = re.findall(r"\d+", r[col["Grid Size"]])
+        ent["grid"] = float(g[0]) * float(g[1]) * float(g[2]) if len(g) == 3 else 0.0
+        for metric, short in WANT.items():
+            if metric not in col or short == "grid":
                 continue
-            kid = r["ID"]
-            ent = rows.setdefault(kid, {"name": r["Kernel Name"]})
             try:
-                val = float(r["Metric Value"].replace(",", ""))
+                val = float(r[col[metric]].replace(",", ""))
             except ValueError:
                 continue
-            ent[WANT[metric]] = val * UNIT_SCALE.get(r.get("Metric Unit", ""), 1.0)
+            ent[short] = val * UNIT_SCALE.get(units[col[metric]], 1.0)
+        rows[r[col["ID"]]] = ent
     agg = {}
     for ent in rows.values():
         cls = classify(ent["name"], ent.get("grid", 0))

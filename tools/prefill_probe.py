@@ -19,7 +19,7 @@ for n in lens:
     ids = torch.randint(3, arch.vocab - 1, (n,), generator=g).tolist()
     best = 1e9
     for rep in range(3):
-        eng.begin(exit_layer=8, max_steps=8, eos_token_ids=[arch.vocab - 1])
+        eng.begin(exit_layer=min(8, arch.layers), max_steps=8, eos_token_ids=[arch.vocab - 1])
         eng.prefill(ids)
         best = min(best, eng.last_device_ms)
     print(f"prefill {n} tokens: {best:.3f} ms (tcgen05 path: {eng.prefill_tc})", flush=True)

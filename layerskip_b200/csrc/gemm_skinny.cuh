@@ -197,12 +197,20 @@ __device__ __forceinline__ void gemm_load_x_bf16(const GemmArgs& a, unsigned cha
   const int cols = min(a.K - col0, kc_cols);
   const int nvec = cols >> 3;                // uint4 (8 bf16) per row
   const int zvec = kc_cols >> 3;
-  for (int m = 0; m < a.xs_rows; ++m) {
+  // four rows per step: their loads are issued together (one L2 round trip per step instead of
+  // one per row — at 7 rows the row-by-row loop cost ~3 us of a 14 us kernel, ncu r2)
+  for (int m0 = 0; m0 < a.xs_rows; m0 += 4) {
     for (int idx = ltid; idx < zvec; idx += nthreads) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (m < a.M && idx < nvec)
-        v = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)m * a.xb_ld + col0 + idx * 8);
-      *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = v;
+      uint4 v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = make_uint4(0, 0, 0, 0);
+        if (m0 + r < a.M && idx < nvec)
+          v[r] = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)(m0 + r) * a.xb_ld + col0 + idx * 8);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (m0 + r < a.xs_rows) *reinterpret_cast<uint4*>(xs + (size_t)(m0 + r) * XS + idx * 16) = v[r];
     }
   }
 }
@@ -222,6 +230,70 @@ __device__ __forceinline__ void gemm_preload_norm(const GemmArgs& a, int wtid, u
   }
 }
 
+// ROWS residual rows at a time: each thread pulls its VEC float4 slices of all ROWS rows into
+// registers at once, the group's sums of squares are reduced across the work threads (2 barriers),
+// and the rows are normalised out of registers into the activation block.
+template <int NT, int ROWS, int VEC>
+__device__ __forceinline__ void rms_rows_group(const GemmArgs& a, unsigned char* xs, int XS, int kc_cols,
+                                               float* stat, int wtid, int swarp, int lane,
+                                               const uint2 (&wreg)[4]) {
+  constexpr int kStatWarps = kGemmWarps + kEpiWarps;
+  const int nvec = a.K >> 2;
+#pragma unroll 1
+  for (int m0 = 0; m0 < a.xs_rows; m0 += ROWS) {
+    float4 v[ROWS][VEC];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)(m0 + r) * a.x_ld);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int idx = wtid + i * kWorkThreads;
+        v[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < a.M && idx < nvec) v[r][i] = xr[idx];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        ss += v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y + v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w;
+      ss = warp_sum(ss);
+      if (lane == 0) stat[swarp * (NT * 8) + m0 + r] = ss;
+    }
+    bar_sync(BAR_WORK, kWorkThreads);
+    if (wtid < ROWS) {
+      float tot = 0.f;
+      for (int w = 0; w < kStatWarps; ++w) tot += stat[w * (NT * 8) + m0 + wtid];
+      stat[kStatWarps * NT * 8 + m0 + wtid] = rsqrtf(tot / (float)a.K + a.eps);
+    }
+    bar_sync(BAR_WORK, kWorkThreads);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int m = m0 + r;
+      if (m >= a.xs_rows) continue;
+      if (m < a.M) {
+        const float rstd = stat[kStatWarps * NT * 8 + m];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const int idx = wtid + i * kWorkThreads;
+          if (idx < nvec) {
+            const float4 x4 = v[r][i];
+            const uint2 wv = wreg[i];
+            uint2 o;
+            o.x = pack_bf16x2(bf16_lo(wv.x) * (x4.x * rstd), bf16_hi(wv.x) * (x4.y * rstd));
+            o.y = pack_bf16x2(bf16_lo(wv.y) * (x4.z * rstd), bf16_hi(wv.y) * (x4.w * rstd));
+            *reinterpret_cast<uint2*>(xs + (size_t)m * XS + idx * 8) = o;
+          }
+        }
+      } else {
+        for (int idx = wtid; idx < (kc_cols >> 3); idx += kWorkThreads)
+          *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
 template <int NT, int PRO>
 __device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& c, int epi,
                                               int wtid, int swarp, int lane, const uint2 (&wreg)[4]) {
@@ -232,53 +304,14 @@ __device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& 
   float* stat = reinterpret_cast<float*>(c.scratch + L.stat);
   constexpr int kStatWarps = kGemmWarps + kEpiWarps;
   if (PRO == PRO_RMS) {
-    // Two passes over the (L1/L2-resident) residual rows: sum of squares, then normalise ->
-    // bf16 (rounding point of a bf16 HF model: modeling_llama.py:52-70).  n_chunks == 1 here.
-    const int nvec = a.K >> 2;  // float4 per row
-    // the norm weights arrive in registers (wreg) so that pass 2 only touches L1-resident rows:
-    // ONE dependent L2/HBM round trip instead of two
-#pragma unroll 1
-    for (int m = 0; m < NT * 8; ++m) {
-      float ss = 0.f;
-      if (m < a.M) {
-        const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)m * a.x_ld);
-        for (int idx = wtid; idx < nvec; idx += kWorkThreads) {
-          const float4 v = xr[idx];
-          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
-      }
-      ss = warp_sum(ss);
-      if (lane == 0) stat[swarp * (NT * 8) + m] = ss;
-    }
-    bar_sync(BAR_WORK, kWorkThreads);
-    if (wtid < NT * 8) {
-      float tot = 0.f;
-      for (int w = 0; w < kStatWarps; ++w) tot += stat[w * (NT * 8) + wtid];
-      stat[kStatWarps * NT * 8 + wtid] = rsqrtf(tot / (float)a.K + a.eps);
-    }
-    bar_sync(BAR_WORK, kWorkThreads);
-#pragma unroll 1
-    for (int m = 0; m < a.xs_rows; ++m) {
-      if (m < a.M) {
-        const float rstd = stat[kStatWarps * NT * 8 + m];
-        const float4* xr = reinterpret_cast<const float4*>(a.x_f32 + (size_t)m * a.x_ld);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = wtid + i * kWorkThreads;
-          if (idx < nvec) {
-            const float4 v = xr[idx];
-            const uint2 wv = wreg[i];
-            uint2 o;
-            o.x = pack_bf16x2(bf16_lo(wv.x) * (v.x * rstd), bf16_hi(wv.x) * (v.y * rstd));
-            o.y = pack_bf16x2(bf16_lo(wv.y) * (v.z * rstd), bf16_hi(wv.y) * (v.w * rstd));
-            *reinterpret_cast<uint2*>(xs + (size_t)m * XS + idx * 8) = o;
-          }
-        }
-      } else {
-        for (int idx = wtid; idx < (kc_cols >> 3); idx += kWorkThreads)
-          *reinterpret_cast<uint4*>(xs + (size_t)m * XS + idx * 16) = make_uint4(0, 0, 0, 0);
-      }
-    }
+    // RMSNorm of the fp32 residual rows -> bf16 (rounding point of a bf16 HF model:
+    // modeling_llama.py:52-70).  n_chunks == 1 here.  Rows are processed FOUR at a time: each thread
+    // pulls its <= 4 float4 slices of all four rows into registers at once (one L2 round trip per
+    // group instead of two per row: the row-by-row version spent ~5 us of a 39 us gate/up launch in
+    // this prologue at 7 rows, ncu r2), reduces, and normalises out of registers.
+    // K <= 4864: 2 slices per thread and row -> groups of 4 rows; larger K: 4 slices -> groups of 2
+    if ((a.K >> 2) <= 2 * kWorkThreads) rms_rows_group<NT, 4, 2>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
+    else rms_rows_group<NT, 2, 4>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
   } else if (a.n_chunks == 1) {
     gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, 0, wtid, kWorkThreads);
   }

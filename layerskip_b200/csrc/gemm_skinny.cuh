@@ -473,6 +473,33 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
         }
       }
     }
+    // EPI_QKV: RoPE factors and KV page of this thread's items, fetched BEFORE the tile arrives
+    // (the committed length is constant while the kernel runs) — same idea as old_resid
+    constexpr int kQkvItems = (kMaxTilesPerPass * NT * 64 + kEpiThreads - 1) / kEpiThreads;
+    float2 q_cs[kQkvItems];
+    int q_page[kQkvItems];
+    if (EPI == EPI_QKV) {
+      const int base_pos = *a.base_len + a.pos_off;
+      const int half = a.head_dim >> 1;
+#pragma unroll
+      for (int k = 0; k < kQkvItems; ++k) {
+        const int itx = etid + k * kEpiThreads;
+        q_cs[k] = make_float2(1.f, 0.f);
+        q_page[k] = 0;
+        if (itx < TPP * NT * 64) {
+          const int tok = itx & 7, r = (itx >> 3) & 7, n = (itx >> 6) % NT, j = (itx >> 6) / NT;
+          const int m = n * 8 + tok, tile = slot * TPP + j;
+          if (m < a.M && tile < a.n_tiles) {
+            const int pr = tile * 16, pos = base_pos + m;
+            if (pr < a.q_rows + a.kv_rows) {
+              const int rel = pr < a.q_rows ? pr : pr - a.q_rows;
+              q_cs[k] = a.rope[(size_t)pos * half + ((rel % a.head_dim) >> 4) * 8 + r];
+            }
+            if (pr >= a.q_rows) q_page[k] = a.page_table[pos >> 6];
+          }
+        }
+      }
+    }
     bar_sync(BAR_FULL0 + buf, kWorkThreads);
     const float* rbase = red + buf * kRedFloats;
     auto ksum = [&](int j, int n, int row, int tok) {
@@ -485,7 +512,10 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
 
     if (EPI == EPI_QKV || EPI == EPI_SILU) {
       const int items = TPP * NT * 64;
-      for (int itx = etid; itx < items; itx += kEpiThreads) {
+#pragma unroll
+      for (int kq = 0; kq < kQkvItems; ++kq) {
+        const int itx = etid + kq * kEpiThreads;
+        if (itx >= items) continue;
         const int tok = itx & 7, r = (itx >> 3) & 7, n = (itx >> 6) % NT, j = (itx >> 6) / NT;
         const int m = n * 8 + tok;
         const int tile = slot * TPP + j;
@@ -503,7 +533,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
             const int rel = is_q ? pr : pr - a.q_rows;
             const int head = rel / HD, tt = (rel % HD) >> 4;
             const int d = tt * 8 + r;
-            const float2 cs = a.rope[(size_t)pos * half + d];
+            const float2 cs = q_cs[kq];
             const float o_lo = lo * cs.x - hi * cs.y;
             const float o_hi = hi * cs.x + lo * cs.y;
             if (is_q) {
@@ -511,14 +541,14 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmArgs& a, const Gemm
               qd[d] = __float2bfloat16_rn(o_lo);
               qd[d + half] = __float2bfloat16_rn(o_hi);
             } else {
-              const int page = a.page_table[pos >> 6];
+              const int page = q_page[kq];
               a.kpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d)] = __float2bfloat16_rn(o_lo);
               a.kpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d + half)] = __float2bfloat16_rn(o_hi);
             }
           } else {                                       // v: natural order, no rotation
             const int rel = pr - a.q_rows - a.kv_rows;
             const int head = rel / HD, d0 = rel % HD;
-            const int page = a.page_table[pos >> 6];
+            const int page = q_page[kq];
             a.vpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d0 + r)] = __float2bfloat16_rn(lo);
             a.vpool[kv_elem_offset(HD, page, a.n_kv_heads, head, pos & 63, d0 + r + 8)] = __float2bfloat16_rn(hi);
           }

@@ -93,6 +93,9 @@ typedef struct {
   float temperature;
   int32_t top_k;
   float top_p;
+  int32_t no_repeat_ngram_size; /* > 0: NoRepeatNGramLogitsProcessor on the device (generator_base.py:77-85;
+                              * transformers logits_process.py _calc_banned_ngram_tokens) over
+                              * prompt + output + drafts; 0 = off                              */
   uint64_t seed;             /* counter-based RNG seed for the sampling path                 */
 } lsk_generation;
 

@@ -57,7 +57,7 @@ class lsk_generation(C.Structure):
     _fields_ = [("exit_layer", C.c_int32), ("max_steps", C.c_int32), ("n_eos", C.c_int32),
                 ("eos_ids", C.c_int32 * LSK_MAX_EOS), ("sample", C.c_int32),
                 ("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float),
-                ("seed", C.c_uint64)]
+                ("no_repeat_ngram_size", C.c_int32), ("seed", C.c_uint64)]
 
 
 class lsk_round_out(C.Structure):

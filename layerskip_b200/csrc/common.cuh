@@ -137,7 +137,7 @@ struct DevState {
   int len;                    // committed KV length (= n_prompt + n_out - 1 once generating)
   int n_out;                  // tokens emitted so far (before EOS truncation)
   int step_count;             // rounds / AR steps executed (RNG stream position)
-  int pad0;
+  int n_prompt;               // prompt length: hist[n_prompt + n_out] is where the next emitted token goes
   int tok[kMaxRows + 1];
   int verified[kMaxRows + 1];
 };

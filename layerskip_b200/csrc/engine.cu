@@ -142,6 +142,8 @@ struct lsk_engine {
   int* cand_idx = nullptr;
   float* gath_val = nullptr;           // TP: [tp_size][16]
   int* gath_idx = nullptr;
+  float* ban_val = nullptr;            // n-gram ban: [16] arg-max of the banned logits rows (n_cand == 1 layout)
+  int* ban_idx = nullptr;
   float* rank_val = nullptr;           // TP: [16]
   int* rank_idx = nullptr;
   int* d_zero = nullptr;
@@ -154,6 +156,9 @@ struct lsk_engine {
   GemmPlan p_qkv, p_o, p_gu, p_d, p_lm;
   size_t l2_prefetch_bytes = 0;          // LSK_L2_PREFETCH_MB: head of the NEXT kernel's weights pulled into L2 (A/B: no gain, +11 % traffic -> off)
   int lm_cand = 0;                     // candidates produced by the LM head (its grid)
+  const float* cur_cand_val = nullptr;  // candidates of the last enqueued LM head (epilogue's, or the banned rows' arg-max)
+  const int* cur_cand_idx = nullptr;
+  int cur_n_cand = 0;
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -661,31 +666,38 @@ static int emit_finalize(lsk_engine* e, int slot, float* dst_row) {
             e->state, slot, (const __nv_bfloat16*)e->embed, c.hidden, dst_row));
   return LSK_OK;
 }
+// token history (prompt ids + emitted tokens) is kept on the device only when the n-gram ban needs it
+static int* hist_ptr(lsk_engine* e) { return e->gen.no_repeat_ngram_size > 0 ? e->d_prompt : nullptr; }
 static int emit_accept(lsk_engine* e, int d_spec, int seq) {
   e->cur_class = CLS_MISC;
   CU(launch(e, accept_greedy_kernel, dim3(1), dim3(256), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), d_spec,
-            e->state, (const GenParams*)e->gen_dev, e->res_dev, seq));
+            e->state, (const GenParams*)e->gen_dev, e->res_dev, seq, hist_ptr(e)));
   return LSK_OK;
 }
 static int emit_ar_commit(lsk_engine* e, int seq) {
   e->cur_class = CLS_MISC;
   CU(launch(e, ar_commit_kernel, dim3(1), dim3(32), 0, cand_val_ptr(e), cand_idx_ptr(e), n_cand(e), e->state,
-            e->res_dev, seq));
+            e->res_dev, seq, hist_ptr(e)));
   return LSK_OK;
 }
 
 // final RMSNorm + LM head on rows [row0, row0+M): arg-max candidates (and optional logits).
 // (llama_model_utils.py:204-205, 271-273, 386-387).  Afterwards e->cand_* / n_cand() hold one
 // (value, index) per candidate per row.
-static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W = nullptr, size_t after_bytes = 0) {
+// With no_repeat_ngram_size > 0 (NoRepeatNGramLogitsProcessor, generator_base.py:77-85) the logits
+// are materialised, the tokens that would repeat an n-gram of the sequence so far are set to -inf
+// (row r continues prompt ++ output ++ draft[0 .. j0 + r)), and the arg-max is taken from the
+// banned rows instead of the LM-head epilogue.
+static int enqueue_lm_head(lsk_engine* e, int row0, int M, int j0, const void* after_W = nullptr, size_t after_bytes = 0) {
   const lsk_config& c = e->cfg;
+  const bool ban = e->gen.no_repeat_ngram_size > 0;
   e->cur_class = CLS_LMHEAD;
   GemmArgs a{};
   a.W = reinterpret_cast<const uint4*>(e->lm_head);
   a.M = M;
   a.x_f32 = e->hidden + (size_t)row0 * c.hidden; a.x_ld = c.hidden;
   a.norm_w = e->final_norm; a.eps = c.rms_eps;
-  a.logits = (e->keep_logits || e->gen.sample) ? e->logits : nullptr; a.logits_ld = e->vocab_l_pad;
+  a.logits = (e->keep_logits || e->gen.sample || ban) ? e->logits : nullptr; a.logits_ld = e->vocab_l_pad;
   a.n_valid_rows = e->vocab_l; a.vocab_off = e->vocab_off;
   a.part_val = e->cand_val; a.part_idx = e->cand_idx;
   a.next_W = after_W;
@@ -702,6 +714,19 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
     }
   } else if (!(e->ablate & (1u << CLS_LMHEAD))) TRY((launch_gemm<PRO_RMS, EPI_LMHEAD>(e, e->p_lm, a)));
   e->cur_class = CLS_MISC;
+  const float* cv = e->cand_val;
+  const int* ci = e->cand_idx;
+  int ncand = e->lm_cand;
+  if (ban) {
+    CU(launch(e, ngram_ban_kernel, dim3(M), dim3(256), 0, e->logits, e->vocab_l_pad, e->vocab_l, e->vocab_off,
+              (const int*)e->d_prompt, (const DevState*)e->state, (int)e->gen.no_repeat_ngram_size, j0));
+    if (!e->gen.sample) {
+      CU(launch(e, argmax_rows_kernel, dim3(M), dim3(1024), 0, (const float*)e->logits, e->vocab_l_pad, e->vocab_l,
+                e->vocab_off, e->ban_val, e->ban_idx));
+      cv = e->ban_val; ci = e->ban_idx; ncand = 1;
+    }
+  }
+  e->cur_cand_val = cv; e->cur_cand_idx = ci; e->cur_n_cand = ncand;
   if (c.tp_size > 1 && e->gen.sample) {
     // every rank needs the whole distribution: all-gather the vocab shards of the M rows, lay them
     // out as [M][vocab]; all ranks then run the same warp / Philox draw and stay in lockstep
@@ -712,19 +737,18 @@ static int enqueue_lm_head(lsk_engine* e, int row0, int M, const void* after_W =
     e->cur_class = CLS_MISC;
   }
   if (c.tp_size > 1 && e->peer_ok) {
-    CU(launch(e, tp_gather_best_kernel, dim3(1), dim3(256), 0, e->peer, (const float*)e->cand_val,
-              (const int*)e->cand_idx, e->lm_cand, M, e->gath_val, e->gath_idx));
+    CU(launch(e, tp_gather_best_kernel, dim3(1), dim3(256), 0, e->peer, cv, ci, ncand, M, e->gath_val, e->gath_idx));
   } else if (c.tp_size > 1) {
-    CU(launch(e, rank_best_kernel, dim3(1), dim3(256), 0, (const float*)e->cand_val,
-              (const int*)e->cand_idx, e->lm_cand, M, e->rank_val, e->rank_idx));
+    CU(launch(e, rank_best_kernel, dim3(1), dim3(256), 0, cv, ci, ncand, M, e->rank_val, e->rank_idx));
     NC(ncclAllGather(e->rank_val, e->gath_val, kMaxRows, ncclFloat, e->comm, e->stream));
     NC(ncclAllGather(e->rank_idx, e->gath_idx, kMaxRows, ncclInt32, e->comm, e->stream));
   }
   return LSK_OK;
 }
-static const float* cand_val_ptr(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->gath_val : e->cand_val; }
-static const int* cand_idx_ptr(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->gath_idx : e->cand_idx; }
-static int n_cand(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->cfg.tp_size : e->lm_cand; }
+// candidates of the LAST enqueued LM head (what the following finalize / accept kernel consumes)
+static const float* cand_val_ptr(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->gath_val : e->cur_cand_val; }
+static const int* cand_idx_ptr(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->gath_idx : e->cur_cand_idx; }
+static int n_cand(lsk_engine* e) { return e->cfg.tp_size > 1 ? e->cfg.tp_size : e->cur_n_cand; }
 
 // ---------------------------------------------------------------------------------------------
 // round / AR-step command streams
@@ -746,7 +770,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   };
   for (int i = 0; i < d; ++i) {
     for (int l = 0; l < E; ++l) TRY(layer_then(l, i, 1, i, E));
-    TRY(enqueue_lm_head(e, i, 1, e->layers[0].wqkv, qkv_bytes));
+    TRY(enqueue_lm_head(e, i, 1, i, e->layers[0].wqkv, qkv_bytes));
     e->cur_class = CLS_MISC;
     if (!e->gen.sample) {
       TRY(emit_finalize(e, 1 + i, e->hidden + (size_t)(i + 1) * c.hidden));
@@ -768,7 +792,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
   }
   // ... then layers >= E see [exit rows of the draft steps ; that row] = rows 0..d (:363-383)
   for (int l = E; l < c.n_layers; ++l) TRY(layer_then(l, 0, d + 1, 0, c.n_layers));
-  TRY(enqueue_lm_head(e, 0, d + 1, e->layers[0].wqkv, qkv_bytes));
+  TRY(enqueue_lm_head(e, 0, d + 1, 0, e->layers[0].wqkv, qkv_bytes));
   e->cur_class = CLS_MISC;
   if (!e->gen.sample) {
     TRY(emit_accept(e, d, seq));
@@ -778,7 +802,7 @@ static int enqueue_round(lsk_engine* e, int E, int d, int seq) {
               e->probs_v, &e->state->verified[0], (int)RNG_VERIFY, 0));
     CU(launch(e, accept_sample_kernel, dim3(1), dim3(kSampleThreads), 0, (const float*)e->probs_d,
               (const float*)e->probs_v, c.vocab, d, e->state, (const GenParams*)e->gen_dev, e->res_dev,
-              e->samp_scratch, seq));
+              e->samp_scratch, seq, hist_ptr(e)));
   }
   return LSK_OK;
 }
@@ -793,7 +817,7 @@ static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
     if (l + 1 < n_layers_run) TRY(enqueue_layer(e, l, 0, 1, len, 0, e->layers[l + 1].wqkv, qkv_bytes));
     else TRY(enqueue_layer(e, l, 0, 1, len, 0, e->lm_head, lm_bytes));
   }
-  TRY(enqueue_lm_head(e, 0, 1, e->layers[0].wqkv, qkv_bytes));
+  TRY(enqueue_lm_head(e, 0, 1, 0, e->layers[0].wqkv, qkv_bytes));
   e->cur_class = CLS_MISC;
   if (!e->gen.sample) {
     TRY(emit_ar_commit(e, seq));
@@ -801,7 +825,7 @@ static int enqueue_ar(lsk_engine* e, int n_layers_run, int seq) {
     CU(launch(e, warp_and_sample_kernel, dim3(1), dim3(kSampleThreads), 0, samp_logits(e),
               samp_ld(e), c.vocab, (const GenParams*)e->gen_dev, (const DevState*)e->state,
               e->probs_v, &e->state->verified[0], (int)RNG_VERIFY, 0));
-    CU(launch(e, ar_commit_sampled_kernel, dim3(1), dim3(32), 0, e->state, e->res_dev, seq));
+    CU(launch(e, ar_commit_sampled_kernel, dim3(1), dim3(32), 0, e->state, e->res_dev, seq, hist_ptr(e)));
   }
   return LSK_OK;
 }
@@ -1036,6 +1060,8 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   TRY(alloc((void**)&e->cand_idx, (size_t)e->sm_count * kMaxRows * 4));
   TRY(alloc((void**)&e->gath_val, (size_t)c.tp_size * kMaxRows * 4));
   TRY(alloc((void**)&e->gath_idx, (size_t)c.tp_size * kMaxRows * 4));
+  TRY(alloc((void**)&e->ban_val, kMaxRows * 4));
+  TRY(alloc((void**)&e->ban_idx, kMaxRows * 4));
   TRY(alloc((void**)&e->rank_val, kMaxRows * 4));
   TRY(alloc((void**)&e->rank_idx, kMaxRows * 4));
   TRY(alloc((void**)&e->d_zero, 4));
@@ -1099,7 +1125,7 @@ void lsk_destroy(lsk_engine* e) {
   }
   void* ptrs[] = {e->embed, e->final_norm, e->lm_head, e->lm_head_tc, e->kpool, e->vpool, e->page_table, e->rope,
                   e->hidden, e->qbuf, e->attn_out, e->act, e->tp_buf, e->logits, e->logits_gath, e->logits_full, e->probs_d, e->probs_v, e->samp_scratch, e->cand_val,
-                  e->cand_idx, e->gath_val, e->gath_idx, e->rank_val, e->rank_idx,
+                  e->cand_idx, e->gath_val, e->gath_idx, e->ban_val, e->ban_idx, e->rank_val, e->rank_idx,
                   e->d_zero, e->d_prompt, e->state, e->gen_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->res_host) cudaFreeHost(e->res_host);
@@ -1328,6 +1354,12 @@ int lsk_begin(lsk_engine* e, const lsk_generation* gen) {
   if (!lsk_weights_complete(e)) return fail(LSK_ERR_STATE, "weights not fully loaded");
   if (gen->n_eos < 0 || gen->n_eos > LSK_MAX_EOS) return fail(LSK_ERR_INVALID, "n_eos out of range");
   if (gen->exit_layer > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "exit_layer > n_layers");
+  if (gen->no_repeat_ngram_size < 0 || gen->no_repeat_ngram_size > 16)
+    return fail(LSK_ERR_INVALID, "no_repeat_ngram_size must be in [0, 16]");
+  if (gen->no_repeat_ngram_size > 0 && !e->logits) {
+    cudaError_t er = cudaMalloc((void**)&e->logits, (size_t)kMaxRows * e->vocab_l_pad * 4);
+    if (er != cudaSuccess) return fail(LSK_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(er));
+  }
   if (gen->sample) {
     if (!(gen->temperature > 0.f)) return fail(LSK_ERR_INVALID, "temperature must be > 0");
     auto alloc0 = [&](float** p, size_t n) -> int {
@@ -1389,7 +1421,7 @@ int lsk_prefill(lsk_engine* e, const int32_t* ids, int32_t n) {
                           (size_t)(e->q_rows + 2 * e->kv_rows) * c.hidden * 2));
     }
   }
-  set_state_kernel<<<1, 1, 0, e->stream>>>(e->state, n - 1, ids[n - 1], 0);
+  set_state_kernel<<<1, 1, 0, e->stream>>>(e->state, n - 1, ids[n - 1], 0, n);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->ev1, e->stream));
   CU(cudaEventSynchronize(e->ev1));
@@ -1421,7 +1453,8 @@ int lsk_round(lsk_engine* e, int32_t d_req, lsk_round_out* out) {
   if (E < 1 || E > e->cfg.n_layers) return fail(LSK_ERR_INVALID, "self-speculation needs 1 <= exit_layer <= n_layers (got %d)", E);
   if (e->host_len + d_req + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context %d + %d exceeds max_ctx", e->host_len, d_req + 1);
   const int seq = ++e->seq;
-  const long long key = ((long long)E << 20) | ((long long)d_req << 8) | (e->gen.sample ? 4 : 0) | 1;
+  const long long key = ((long long)E << 20) | ((long long)d_req << 8) | (e->gen.sample ? 4 : 0) | 1 |
+                        ((long long)e->gen.no_repeat_ngram_size << 32);
   TRY(run_cached(e, key, [&]() { return enqueue_round(e, E, d_req, 0); }));
   (void)seq;
   TRY(peer_check(e));
@@ -1435,7 +1468,7 @@ int lsk_ar_step(lsk_engine* e, int32_t* token_out) {
   if (!e->prefilled) return fail(LSK_ERR_STATE, "lsk_prefill must precede lsk_ar_step");
   if (e->host_len + 2 > e->max_pos) return fail(LSK_ERR_CTX, "context exceeds max_ctx");
   const int nl = (e->gen.exit_layer > 0 && e->gen.exit_layer <= e->cfg.n_layers) ? e->gen.exit_layer : e->cfg.n_layers;
-  const long long key = ((long long)nl << 20) | (e->gen.sample ? 4 : 0) | 2;
+  const long long key = ((long long)nl << 20) | (e->gen.sample ? 4 : 0) | 2 | ((long long)e->gen.no_repeat_ngram_size << 32);
   TRY(run_cached(e, key, [&]() { return enqueue_ar(e, nl, 0); }));
   TRY(peer_check(e));
   *token_out = e->res_host->emitted_ids[0];
@@ -1497,7 +1530,10 @@ int lsk_debug_forward_rows(lsk_engine* e, const int32_t* ids, int32_t m) {
   for (int l = 0; l < c.n_layers; ++l) TRY(enqueue_layer(e, l, 0, m, &e->state->len, 0));
   const int keep_sample = e->gen.sample;
   e->gen.sample = 0;
-  const int st = enqueue_lm_head(e, 0, m);
+  const int keep_ban = e->gen.no_repeat_ngram_size;
+  e->gen.no_repeat_ngram_size = 0;
+  const int st = enqueue_lm_head(e, 0, m, 0);
+  e->gen.no_repeat_ngram_size = keep_ban;
   e->gen.sample = keep_sample;
   if (st != LSK_OK) return st;
   CU(cudaStreamSynchronize(e->stream));

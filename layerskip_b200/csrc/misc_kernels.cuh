@@ -161,7 +161,7 @@ __device__ __forceinline__ bool is_eos(const GenParams& gp, int tok) {
 // thread-0 part of the greedy accept: compares drafts with the verifier's arg-maxes, commits.
 __device__ __forceinline__ void accept_commit(const int* s_ver, int d, DevState* __restrict__ st,
                                               const GenParams& g, RoundResult* __restrict__ res,
-                                              int seq) {
+                                              int seq, int* __restrict__ hist = nullptr) {
   int d_act = d;
   for (int i = 0; i < d; ++i)
     if (is_eos(g, st->tok[1 + i])) { d_act = i + 1; break; }
@@ -175,6 +175,8 @@ __device__ __forceinline__ void accept_commit(const int* s_ver, int d, DevState*
   for (int i = 0; i < n; ++i) res->emitted_ids[i] = st->tok[1 + i];
   res->emitted_ids[n] = s_ver[n];
   for (int i = 0; i <= d; ++i) st->verified[i] = s_ver[i];
+  if (hist != nullptr)                       // token history for the n-gram ban (prompt ids + output)
+    for (int i = 0; i <= n; ++i) hist[st->n_prompt + st->n_out + i] = res->emitted_ids[i];
   st->len += n + 1;
   st->n_out += n + 1;
   st->tok[0] = s_ver[n];
@@ -187,7 +189,7 @@ __device__ __forceinline__ void accept_commit(const int* s_ver, int d, DevState*
 __global__ void accept_greedy_kernel(const float* __restrict__ cand_val,
                                      const int* __restrict__ cand_idx, int n_cand, int d,
                                      DevState* __restrict__ st, const GenParams* __restrict__ gp,
-                                     RoundResult* __restrict__ res, int seq) {
+                                     RoundResult* __restrict__ res, int seq, int* __restrict__ hist) {
   __shared__ int s_ver[kMaxRows];
   pdl_launch_dependents();
   pdl_wait();
@@ -197,12 +199,13 @@ __global__ void accept_greedy_kernel(const float* __restrict__ cand_val,
     if (lane == 0) s_ver[row] = tok;
   }
   __syncthreads();
-  if (threadIdx.x == 0) accept_commit(s_ver, d, st, *gp, res, seq);
+  if (threadIdx.x == 0) accept_commit(s_ver, d, st, *gp, res, seq, hist);
 }
 
 // Autoregressive commit (autoregressive_generator.py:62-76): token = argmax(row 0).
 __device__ __forceinline__ void ar_commit(int tok, DevState* __restrict__ st,
-                                          RoundResult* __restrict__ res, int seq) {
+                                          RoundResult* __restrict__ res, int seq, int* __restrict__ hist = nullptr) {
+  if (hist != nullptr) hist[st->n_prompt + st->n_out] = tok;
   st->tok[0] = tok;
   st->len += 1;
   st->n_out += 1;
@@ -220,12 +223,12 @@ __device__ __forceinline__ void ar_commit(int tok, DevState* __restrict__ st,
 __global__ void ar_commit_kernel(const float* __restrict__ cand_val,
                                  const int* __restrict__ cand_idx, int n_cand,
                                  DevState* __restrict__ st, RoundResult* __restrict__ res,
-                                 int seq) {
+                                 int seq, int* __restrict__ hist) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x < 32) {
     const int tok = reduce_candidates(cand_val, cand_idx, n_cand, 0, threadIdx.x);
-    if (threadIdx.x == 0) ar_commit(tok, st, res, seq);
+    if (threadIdx.x == 0) ar_commit(tok, st, res, seq, hist);
   }
 }
 
@@ -282,10 +285,82 @@ __global__ void residual_add_kernel(float* __restrict__ hidden, int ld,
   }
 }
 
-__global__ void set_state_kernel(DevState* st, int len, int tok0, int n_out) {
+__global__ void set_state_kernel(DevState* st, int len, int tok0, int n_out, int n_prompt) {
   st->len = len;
   st->tok[0] = tok0;
   st->n_out = n_out;
+  st->n_prompt = n_prompt;
+}
+
+// ---------------------------------------------------------------------------------------
+// NoRepeatNGramLogitsProcessor on the device (transformers generation/logits_process.py:
+// `_calc_banned_ngram_tokens`; the reference builds it at generator_base.py:77-85).  Row `row` of
+// `logits` predicts the token after  seq = hist[0 .. n_prompt + n_out) ++ draft[0 .. j0 + row):
+// every token that would complete an n-gram already present in seq gets -inf.  With
+// len(seq) + 1 < n nothing is banned (HF's early return); n == 1 bans every token already seen.
+// `logits` holds this rank's vocabulary shard [vocab_off, vocab_off + v_local).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ngram_ban_kernel(float* __restrict__ logits, int ld, int v_local, int vocab_off, const int* __restrict__ hist,
+                 const DevState* __restrict__ st, int n, int j0) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x, j = j0 + row;
+  const int hlen = st->n_prompt + st->n_out;
+  const int L = hlen + j;                                   // tokens in seq
+  if (L + 1 < n) return;
+  auto tok_at = [&](int i) { return i < hlen ? hist[i] : st->tok[1 + i - hlen]; };
+  float* lrow = logits + (size_t)row * ld;
+  for (int i = threadIdx.x; i + n - 1 < L; i += blockDim.x) {   // n-gram seq[i .. i+n-1] exists
+    bool same = true;
+    for (int k = 0; k < n - 1 && same; ++k) same = tok_at(i + k) == tok_at(L - (n - 1) + k);
+    if (same) {
+      const int banned = tok_at(i + n - 1) - vocab_off;
+      if (banned >= 0 && banned < v_local) lrow[banned] = -INFINITY;
+    }
+  }
+}
+
+// arg-max of every logits row (lowest index wins ties) -> one candidate per row, in the layout the
+// finalize / accept kernels consume with n_cand == 1.  Used when the logits had to be materialised
+// (n-gram ban) instead of taking the arg-max inside the LM-head epilogue.
+__global__ void __launch_bounds__(1024)
+argmax_rows_kernel(const float* __restrict__ logits, int ld, int v_local, int vocab_off,
+                   float* __restrict__ out_val, int* __restrict__ out_idx) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x;
+  const float* lrow = logits + (size_t)row * ld;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < v_local; c += blockDim.x) {
+    const float v = lrow[c];
+    if (better(v, c, bv, bi)) { bv = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bv = s_v[threadIdx.x];
+    bi = s_i[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      out_val[row] = bv;
+      out_idx[row] = (bi == 0x7fffffff) ? 0x7fffffff : bi + vocab_off;
+    }
+  }
 }
 
 }  // namespace lsk

@@ -262,7 +262,8 @@ warp_and_sample_kernel(const float* __restrict__ logits, int ld, int V,
 __global__ void __launch_bounds__(kSampleThreads)
 accept_sample_kernel(const float* __restrict__ p_draft, const float* __restrict__ p_verify, int V,
                      int d, DevState* __restrict__ st, const GenParams* __restrict__ gpp,
-                     RoundResult* __restrict__ res, float* __restrict__ scratch, int seq) {
+                     RoundResult* __restrict__ res, float* __restrict__ scratch, int seq,
+                     int* __restrict__ hist) {
   __shared__ float red[96 + 32];
   __shared__ int s_pick;
   __shared__ int s_n, s_dact, s_reject;
@@ -306,6 +307,8 @@ accept_sample_kernel(const float* __restrict__ p_draft, const float* __restrict_
     res->verified_ids[n] = bonus;
     for (int i = 0; i < n; ++i) res->emitted_ids[i] = st->tok[1 + i];
     res->emitted_ids[n] = bonus;
+    if (hist != nullptr)
+      for (int i = 0; i <= n; ++i) hist[st->n_prompt + st->n_out + i] = res->emitted_ids[i];
     st->len += n + 1;
     st->n_out += n + 1;
     st->tok[0] = bonus;
@@ -318,11 +321,12 @@ accept_sample_kernel(const float* __restrict__ p_draft, const float* __restrict_
 
 // AR commit when the token was sampled into st->verified[0].
 __global__ void ar_commit_sampled_kernel(DevState* __restrict__ st, RoundResult* __restrict__ res,
-                                         int seq) {
+                                         int seq, int* __restrict__ hist) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) {
     const int tok = st->verified[0];
+    if (hist != nullptr) hist[st->n_prompt + st->n_out] = tok;
     st->tok[0] = tok;
     st->len += 1;
     st->n_out += 1;

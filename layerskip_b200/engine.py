@@ -147,13 +147,14 @@ class Engine:
     # ------------------------------------------------------------------ generation
     def begin(self, exit_layer: int, max_steps: int, eos_token_ids: Sequence[int],
               sample: bool = False, temperature: float = 0.6, top_k: int = 0, top_p: float = 0.9,
-              seed: int = 0) -> None:
+              seed: int = 0, no_repeat_ngram_size: int = 0) -> None:
         eos = list(eos_token_ids)
         if len(eos) > _lib.LSK_MAX_EOS:
             raise ValueError(f"at most {_lib.LSK_MAX_EOS} eos ids are supported")
         gen = _lib.lsk_generation(exit_layer=exit_layer, max_steps=max_steps, n_eos=len(eos),
                                   sample=int(bool(sample)), temperature=temperature, top_k=top_k,
-                                  top_p=top_p, seed=seed)
+                                  top_p=top_p, seed=seed,
+                                  no_repeat_ngram_size=int(no_repeat_ngram_size or 0))
         for i, t in enumerate(eos):
             gen.eos_ids[i] = int(t)
         with torch.cuda.device(self.device):

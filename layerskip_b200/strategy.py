@@ -96,11 +96,25 @@ def _check_context(eng, n_prompt: int, cfg: GenerationConfig) -> None:
                          "larger max_ctx")
 
 
-def _reject_unsupported(logits_processors) -> None:
-    if logits_processors:
-        raise NotImplementedError(
-            "logits_processors (--no_repeat_ngram_size) would need the logits on the host every "
-            "step; the B200 engine keeps them on chip and has no CPU fallback")
+def _ngram_size_of(logits_processors) -> int:
+    """The reference builds at most ONE logits processor: HF's `NoRepeatNGramLogitsProcessor`
+    (`generator_base.py:77-85`, from `--no_repeat_ngram_size`).  The engine applies it on the device
+    (csrc/misc_kernels.cuh: ngram_ban_kernel) over the whole sequence so far — prompt, output and the
+    round's drafts — which is HF's documented semantics.  (The reference itself hands the processor
+    only the current step's `input_ids`, a single token after the first step, so its ban list is
+    empty from then on: INTEGRATION.md.)  Any other processor would need the logits on the host:
+    refused, there is no CPU fallback."""
+    size = 0
+    for proc in (logits_processors or []):
+        n = getattr(proc, "ngram_size", None)
+        if type(proc).__name__ != "NoRepeatNGramLogitsProcessor" or not isinstance(n, int) or n <= 0:
+            raise NotImplementedError(
+                f"logits processor {type(proc).__name__} is not supported: only NoRepeatNGramLogitsProcessor "
+                "runs on the device; the B200 engine keeps the logits on chip and has no CPU fallback")
+        if n > 16:
+            raise NotImplementedError("no_repeat_ngram_size > 16 is not supported")
+        size = n if size == 0 else min(size, n)
+    return size
 
 
 class B200SelfSpeculativeGenerationStrategy(GenerationStrategy):
@@ -116,14 +130,14 @@ class B200SelfSpeculativeGenerationStrategy(GenerationStrategy):
     def generate_token_ids(self, model, input_ids: List[int], eos_token_ids: List[int],
                            generation_config: GenerationConfig, logits_processors=None,
                            stopping_criteria=None, streamer=None) -> GenerationStrategyResult:
-        _reject_unsupported(logits_processors)
+        ngram = _ngram_size_of(logits_processors)
         cfg = generation_config
         eng = self.engines.get(model)
         _check_context(eng, len(input_ids), cfg)
         _check_num_speculations(cfg, eng)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
-                  seed=_generation_seed(self.engines, eng, cfg.sample))
+                  seed=_generation_seed(self.engines, eng, cfg.sample), no_repeat_ngram_size=ngram)
         eng.prefill(input_ids)
         output_ids: List[int] = []
         matches = drafted = 0
@@ -173,13 +187,13 @@ class B200AutoRegressiveGenerationStrategy(GenerationStrategy):
     def generate_token_ids(self, model, input_ids: List[int], eos_token_ids: List[int],
                            generation_config: GenerationConfig, logits_processors=None,
                            stopping_criteria=None, streamer=None) -> GenerationStrategyResult:
-        _reject_unsupported(logits_processors)
+        ngram = _ngram_size_of(logits_processors)
         cfg = generation_config
         eng = self.engines.get(model)
         _check_context(eng, len(input_ids), cfg)
         eng.begin(exit_layer=cfg.exit_layer, max_steps=cfg.max_steps, eos_token_ids=eos_token_ids,
                   sample=cfg.sample, temperature=cfg.temperature, top_k=cfg.top_k, top_p=cfg.top_p,
-                  seed=_generation_seed(self.engines, eng, cfg.sample))
+                  seed=_generation_seed(self.engines, eng, cfg.sample), no_repeat_ngram_size=ngram)
         eng.prefill(input_ids)
         output_ids: List[int] = []
         prev = input_ids[-1]

@@ -338,6 +338,28 @@ def warp_top_k_top_p(logits: torch.Tensor, top_k: int, top_p: float) -> torch.Te
     return logits
 
 
+def ban_repeated_ngrams(logits: torch.Tensor, seqs: Sequence[Sequence[int]], n: int) -> torch.Tensor:
+    """HF `NoRepeatNGramLogitsProcessor` (transformers generation/logits_process.py,
+    `_calc_banned_ngram_tokens`; built by the reference at generator_base.py:77-85) with its
+    documented inputs: row r of `logits` continues the FULL token sequence `seqs[r]`; every token that
+    would complete an n-gram already present in that sequence gets -inf.  (The reference hands the
+    processor only the current step's ids — one token after the first step — so that its ban list
+    stays empty; the engine and this oracle implement the processor's documented semantics.)"""
+    if n <= 0:
+        return logits
+    out = logits.clone()
+    for r, seq in enumerate(seqs):
+        seq = list(seq)
+        L = len(seq)
+        if L + 1 < n:
+            continue
+        prefix = tuple(seq[L - (n - 1):]) if n > 1 else ()
+        for i in range(0, L - n + 1):
+            if tuple(seq[i:i + n - 1]) == prefix:
+                out[r, seq[i + n - 1]] = -float("inf")
+    return out
+
+
 def pick_tokens(logits: torch.Tensor, last_only: bool, sample: bool, temperature: float,
                 top_k: int, top_p: float) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """`decode_next_token` (llama_model_utils.py:109-131) on logits [s, V].
@@ -382,7 +404,8 @@ class OracleResult:
 def self_speculative_generate(
         w: OracleWeights, prompt: Sequence[int], eos_token_ids: Sequence[int], *,
         max_steps: int, exit_layer: int, num_speculations: int, sample: bool = False,
-        temperature: float = 0.6, top_k: int = 0, top_p: float = 0.9) -> OracleResult:
+        temperature: float = 0.6, top_k: int = 0, top_p: float = 0.9,
+        no_repeat_ngram_size: int = 0) -> OracleResult:
     """self_speculation_generator.py:32-99 (outer loop) and :102-229 (one round)."""
     prompt = list(prompt)
     kv = KVStore(w.dims.layers)
@@ -402,6 +425,8 @@ def self_speculative_generate(
         for _ in range(d_req):
             logits, exit_rows = step_early(w, feed, kv, exit_layer, exit_rows)
             kv_touched = max(kv_touched, exit_layer)
+            if no_repeat_ngram_size:
+                logits = ban_repeated_ngrams(logits[-1:], [prompt + out + draft], no_repeat_ngram_size)
             tok, prob = pick_tokens(logits, True, sample, temperature, top_k, top_p)
             t = int(tok[0])
             draft.append(t)
@@ -415,6 +440,9 @@ def self_speculative_generate(
         logits = step_remainder(w, cur + draft, kv, exit_layer, exit_rows, kv_touched)
         kv_touched = w.dims.layers
         ver_logits = logits[n_in - 1:]                                            # :177
+        if no_repeat_ngram_size:
+            ver_logits = ban_repeated_ngrams(
+                ver_logits, [prompt + out + draft[:j] for j in range(len(draft) + 1)], no_repeat_ngram_size)
         ver_tok, ver_prob = pick_tokens(ver_logits, False, sample, temperature, top_k, top_p)
         verified = [int(t) for t in ver_tok]
         # ---- accept (:185-199)
@@ -455,7 +483,7 @@ def self_speculative_generate(
 def autoregressive_generate(
         w: OracleWeights, prompt: Sequence[int], eos_token_ids: Sequence[int], *,
         max_steps: int, exit_layer: int = -1, sample: bool = False, temperature: float = 0.6,
-        top_k: int = 0, top_p: float = 0.9) -> OracleResult:
+        top_k: int = 0, top_p: float = 0.9, no_repeat_ngram_size: int = 0) -> OracleResult:
     """autoregressive_generator.py:26-80: `forward` each step, or `forward_early` when
     exit_layer > 0 (:44-51); EOS is checked BEFORE the token is appended (:66-67)."""
     kv = KVStore(w.dims.layers)
@@ -467,6 +495,8 @@ def autoregressive_generate(
             logits, exit_rows = step_early(w, feed, kv, exit_layer, exit_rows)
         else:
             logits = step_all_layers(w, feed, kv)
+        if no_repeat_ngram_size:
+            logits = ban_repeated_ngrams(logits[-1:], [list(prompt) + out], no_repeat_ngram_size)
         tok, _ = pick_tokens(logits, True, sample, temperature, top_k, top_p)
         t = int(tok[0])
         if t in eos_token_ids:

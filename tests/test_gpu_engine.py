@@ -204,6 +204,46 @@ def test_page_table_indirection(strategies):
     assert again.predicted_tokens == base.predicted_tokens
 
 
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_no_repeat_ngram_ban_on_the_device_matches_the_oracle(n, strategies):
+    """`--no_repeat_ngram_size` (generator_base.py:77-85): the device ban list gives the oracle's
+    (= HF processor's) tokens, the continuation never completes an n-gram that is already in the
+    sequence, and speculative == autoregressive still holds exactly."""
+    from transformers.generation.logits_process import LogitsProcessorList, NoRepeatNGramLogitsProcessor
+    spec, ar = strategies
+    case = next(c for c in _engine_cases() if c["name"] == "gqa128_a0.1")
+    dims, model, w = _model_for(case)
+    prompt = [11, 500, 23, 11, 500, 23, 8, 8, 8, 639 - 1, 100]            # repeats inside the prompt
+    procs = LogitsProcessorList([NoRepeatNGramLogitsProcessor(n)])
+    cfg = _gen_cfg(case, max_steps=40)
+    s = spec.generate_token_ids(model, prompt, case["eos"], cfg, logits_processors=procs)
+    a = ar.generate_token_ids(model, prompt, case["eos"], _gen_cfg(case, max_steps=40, exit_layer=-1,
+                                                                  num_speculations=-1), logits_processors=procs)
+    assert s.predicted_tokens == a.predicted_tokens
+    seq = prompt + s.predicted_tokens
+    for pos in range(len(prompt), len(seq)):                  # the token at `pos` never completes a seen n-gram
+        gram = tuple(seq[pos - n + 1: pos + 1])
+        assert all(tuple(seq[i:i + n]) != gram for i in range(0, pos - n + 1)), (n, pos, gram)
+    want = orc.self_speculative_generate(w, prompt, case["eos"], **{**case["cfg"], "max_steps": 40},
+                                         no_repeat_ngram_size=n).predicted_tokens
+    j = next((k for k in range(min(len(want), len(s.predicted_tokens))) if want[k] != s.predicted_tokens[k]),
+             None)
+    if j is not None:                                         # only a near-tie may differ (margin gate)
+        logits = orc.teacher_forced_logits(w, prompt, want[:j + 1])[j:j + 1]
+        row = orc.ban_repeated_ngrams(logits, [prompt + want[:j]], n)[0]
+        assert float(row[want[j]] - row[s.predicted_tokens[j]]) < pu.TAU
+    else:
+        assert len(want) == len(s.predicted_tokens)
+    # sampling with the ban runs and respects it too
+    torch.manual_seed(1)
+    smp = spec.generate_token_ids(model, prompt, case["eos"], _gen_cfg(case, max_steps=40, sample=True),
+                                  logits_processors=procs)
+    seq = prompt + smp.predicted_tokens
+    for pos in range(len(prompt), len(seq)):
+        gram = tuple(seq[pos - n + 1: pos + 1])
+        assert all(tuple(seq[i:i + n]) != gram for i in range(0, pos - n + 1)), ("sample", n, pos)
+
+
 def test_unsupported_inputs_fail_loudly(strategies):
     spec, _ = strategies
     case = _engine_cases()[0]

@@ -172,3 +172,19 @@ def test_context_overflow_is_reported_before_any_kernel_runs():
     with pytest.raises(ValueError, match="max_ctx=256"):
         _check_context(eng, 100, GenerationConfig(max_steps=156))
     _check_context(object(), 10 ** 6, GenerationConfig(max_steps=512))        # engines without the attribute
+
+
+def test_logits_processor_list_is_mapped_to_the_device_ngram_ban():
+    """generator_base.py:77-85 builds at most one processor (NoRepeatNGram); the strategy turns it
+    into the engine's `no_repeat_ngram_size` and refuses anything it cannot run on the device."""
+    from transformers.generation.logits_process import (LogitsProcessorList, NoRepeatNGramLogitsProcessor,
+                                                         TemperatureLogitsWarper)
+    from layerskip_b200.strategy import _ngram_size_of
+    assert _ngram_size_of(None) == 0 and _ngram_size_of([]) == 0 and _ngram_size_of(LogitsProcessorList()) == 0
+    assert _ngram_size_of(LogitsProcessorList([NoRepeatNGramLogitsProcessor(3)])) == 3
+    with pytest.raises(NotImplementedError):
+        _ngram_size_of(LogitsProcessorList([TemperatureLogitsWarper(0.7)]))
+    with pytest.raises(NotImplementedError):
+        _ngram_size_of([lambda ids, scores: scores])
+    with pytest.raises(NotImplementedError):
+        _ngram_size_of([NoRepeatNGramLogitsProcessor(17)])

@@ -197,19 +197,19 @@ __device__ __forceinline__ void gemm_load_x_bf16(const GemmArgs& a, unsigned cha
   const int cols = min(a.K - col0, kc_cols);
   const int nvec = cols >> 3;                // uint4 (8 bf16) per row
   const int zvec = kc_cols >> 3;
-  // eight rows per step: their loads are issued together (one L2 round trip for a whole 7-row
-  // verify block instead of one per row — the row-by-row loop cost ~3 us of a 14 us kernel, ncu r2)
-  for (int m0 = 0; m0 < a.xs_rows; m0 += 8) {
+  // four rows per step: their loads are issued together (one L2 round trip per step instead of
+  // one per row — at 7 rows the row-by-row loop cost ~3 us of a 14 us kernel, ncu r2)
+  for (int m0 = 0; m0 < a.xs_rows; m0 += 4) {
     for (int idx = ltid; idx < zvec; idx += nthreads) {
-      uint4 v[8];
+      uint4 v[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < 4; ++r) {
         v[r] = make_uint4(0, 0, 0, 0);
         if (m0 + r < a.M && idx < nvec)
           v[r] = *reinterpret_cast<const uint4*>(a.x_bf16 + (size_t)(m0 + r) * a.xb_ld + col0 + idx * 8);
       }
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < 4; ++r)
         if (m0 + r < a.xs_rows) *reinterpret_cast<uint4*>(xs + (size_t)(m0 + r) * XS + idx * 16) = v[r];
     }
   }
@@ -309,10 +309,11 @@ __device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& 
     // pulls its <= 4 float4 slices of all four rows into registers at once (one L2 round trip per
     // group instead of two per row: the row-by-row version spent ~5 us of a 39 us gate/up launch in
     // this prologue at 7 rows, ncu r2), reduces, and normalises out of registers.
-    // K <= 4864: 2 slices per thread and row -> groups of 8 rows (one group = one L2 round trip for a
-    // whole 7-row verify block); larger K: 4 slices -> groups of 4
-    if ((a.K >> 2) <= 2 * kWorkThreads) rms_rows_group<NT, 8, 2>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
-    else rms_rows_group<NT, 4, 4>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
+    // K <= 4864: 2 slices per thread and row -> groups of 4 rows; larger K: 4 slices -> groups of 2.
+    // (Groups of 8 rows were measured: the 64 live registers spill inside the 96-register budget of
+    // the 640-thread CTA and the round got 9 % SLOWER, 7.32 vs 6.70 ms.)
+    if ((a.K >> 2) <= 2 * kWorkThreads) rms_rows_group<NT, 4, 2>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
+    else rms_rows_group<NT, 2, 4>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
   } else if (a.n_chunks == 1) {
     gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, 0, wtid, kWorkThreads);
   }

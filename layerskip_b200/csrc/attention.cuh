@@ -81,42 +81,71 @@ __device__ __forceinline__ void team_sync() {
 }
 
 // Fixed-order merge of the splits' partials for one (row, 16-dim segment); `ml(s)` / `o(s)` return
-// split s's (m, l) pair and O segment (a peer CTA's shared memory).
-template <int HD, typename FML, typename FO>
+// split s's (m, l) pair and O segment (a peer CTA's shared memory).  SP = compile-time bound on
+// the number of splits: with SP <= 4 every remote value (4 (m, l) pairs + 16 float4) is requested
+// up front — ONE distributed-shared-memory round trip instead of a chain of five; same arithmetic
+// in the same order either way.
+template <int HD, int SP, typename FML, typename FO>
 __device__ __forceinline__ void merge_splits_write(const AttnArgs& a, int kvh, int row, int dseg,
                                                    FML ml, FO o) {
-  // all (m, l) pairs first, then the O segments in batches of independent loads: 1 + 4 remote
-  // latencies instead of a dependent chain of 2 x n_splits (same arithmetic, same order)
-  float ms[kMaxSplits], ls[kMaxSplits];
+  float ms[SP], ls[SP];
 #pragma unroll
-  for (int s = 0; s < kMaxSplits; ++s) {
+  for (int s = 0; s < SP; ++s) {
     ms[s] = -INFINITY; ls[s] = 0.f;
     if (s < a.n_splits) { const float* p = ml(s); ms[s] = p[0]; ls[s] = p[1]; }
-  }
-  float mm = -INFINITY;
-#pragma unroll
-  for (int s = 0; s < kMaxSplits; ++s) mm = fmaxf(mm, ms[s]);
-  float f[kMaxSplits];
-  float ll = 0.f;
-#pragma unroll
-  for (int s = 0; s < kMaxSplits; ++s) {
-    f[s] = (ms[s] == -INFINITY) ? 0.f : __expf(ms[s] - mm);
-    if (s < a.n_splits) ll += ls[s] * f[s];
   }
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  float ll = 0.f;
+  if (SP <= 4) {
+    float4 v[4][SP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 v[kMaxSplits];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int s = 0; s < kMaxSplits; ++s)
-      v[s] = (s < a.n_splits) ? reinterpret_cast<const float4*>(o(s))[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < SP; ++s)
+        v[i][s] = (s < a.n_splits) ? reinterpret_cast<const float4*>(o(s))[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mm = -INFINITY;
 #pragma unroll
-    for (int s = 0; s < kMaxSplits; ++s) {
-      if (s < a.n_splits) {
-        acc[4 * i] += v[s].x * f[s]; acc[4 * i + 1] += v[s].y * f[s];
-        acc[4 * i + 2] += v[s].z * f[s]; acc[4 * i + 3] += v[s].w * f[s];
+    for (int s = 0; s < SP; ++s) mm = fmaxf(mm, ms[s]);
+    float f[SP];
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      f[s] = (ms[s] == -INFINITY) ? 0.f : __expf(ms[s] - mm);
+      if (s < a.n_splits) ll += ls[s] * f[s];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        if (s < a.n_splits) {
+          acc[4 * i] += v[i][s].x * f[s]; acc[4 * i + 1] += v[i][s].y * f[s];
+          acc[4 * i + 2] += v[i][s].z * f[s]; acc[4 * i + 3] += v[i][s].w * f[s];
+        }
+      }
+  } else {
+    // all (m, l) pairs first, then the O segments in batches of independent loads
+    float mm = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < SP; ++s) mm = fmaxf(mm, ms[s]);
+    float f[SP];
+#pragma unroll
+    for (int s = 0; s < SP; ++s) {
+      f[s] = (ms[s] == -INFINITY) ? 0.f : __expf(ms[s] - mm);
+      if (s < a.n_splits) ll += ls[s] * f[s];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v[SP];
+#pragma unroll
+      for (int s = 0; s < SP; ++s)
+        v[s] = (s < a.n_splits) ? reinterpret_cast<const float4*>(o(s))[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < SP; ++s) {
+        if (s < a.n_splits) {
+          acc[4 * i] += v[s].x * f[s]; acc[4 * i + 1] += v[s].y * f[s];
+          acc[4 * i + 2] += v[s].z * f[s]; acc[4 * i + 3] += v[s].w * f[s];
+        }
       }
     }
   }
@@ -382,10 +411,10 @@ attn_cluster_kernel(const AttnArgs a) {
   constexpr int SEG = HD / 16;
   for (int it = split * kAttnThreads + tid; it < R * SEG; it += a.n_splits * kAttnThreads) {
     const int row = it / SEG, dseg = (it % SEG) * 16;
-    merge_splits_write<HD>(
-        a, kvh, row, dseg,
-        [&](int s) { return (const float*)cluster.map_shared_rank(pml, s) + row * 2; },
-        [&](int s) { return (const float*)cluster.map_shared_rank(po, s) + (size_t)row * HD + dseg; });
+    auto f_ml = [&](int s) { return (const float*)cluster.map_shared_rank(pml, s) + row * 2; };
+    auto f_o = [&](int s) { return (const float*)cluster.map_shared_rank(po, s) + (size_t)row * HD + dseg; };
+    if (a.n_splits <= 4) merge_splits_write<HD, 4>(a, kvh, row, dseg, f_ml, f_o);
+    else merge_splits_write<HD, kMaxSplits>(a, kvh, row, dseg, f_ml, f_o);
   }
   cluster.sync();      // nobody leaves while a peer may still read its partials
 }

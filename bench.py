@@ -306,7 +306,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": f"{w_dtype} (CPU oracle port; the engine arm computes in bf16)",
         "data": "synthetic",
         "config": {"workload": workload_string(args),
@@ -714,11 +714,13 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_dev * 1e3 / max(1, args.steps),
-        "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
+        # the headline series over N is ONE model on N GPUs (tensor parallel): strong scaling, with
+        # N = 1 as its first point; `--replicas` makes the independent-replicas series the headline
+        "higher_is_better": True, "scaling": "weak" if (args.replicas and world > 1) else "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "acceptance_rate": acc_mean,
         "config": {"workload": workload_string(args),
-                   "parallelism": f"tp{tp}" if tp > 1 else f"replicas{world}",
+                   "parallelism": f"tp{tp}" if tp > 1 else ("single-gpu" if world == 1 else f"replicas{world}"),
                    **({"tp_collectives": tp_collectives_name()} if tp > 1 else {}),
                    "l2": "inputs_exceed_l2 (weights 13.5 GB >> 126 MB L2)",
                    "step": "one full generation (prefill + rounds)"},

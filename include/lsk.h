@@ -205,6 +205,17 @@ typedef struct {
 int lsk_plan_gemm(int64_t n_rows, int64_t k, int32_t m, int32_t pro, int32_t epi, int32_t sm_count,
                   lsk_gemm_plan* out);
 
+/* Host-side launch plan of the attention kernel (pure host logic): split-KV factor (an engine
+ * constant: results are batch-invariant only for a fixed partition), K/V ring depth, grid, shared
+ * memory incl. the one-CTA-per-SM floor, 16-row blocks per CTA.  n_heads / n_kv_heads_local are the
+ * tensor-parallel shard's head counts with the same GQA ratio as the model. */
+typedef struct {
+  int32_t ok, n_splits, ring_stages, grid, block, row_blocks, kv_refetched_per_row_block;
+  int64_t smem_bytes, smem_limit;
+} lsk_attn_plan;
+int lsk_plan_attention(int32_t head_dim, int32_t n_heads, int32_t n_kv_heads_local, int32_t m,
+                       int32_t sm_count, lsk_attn_plan* out);
+
 /* Stand-alone kernel entry points used by the micro-benchmarks and unit tests: run the skinny
  * GEMM (y[m, n] = x[m, k] . W[n, k]^T, fp32 out) on packed weights / the split-KV attention on
  * caller-provided device buffers. */

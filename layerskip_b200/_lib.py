@@ -74,6 +74,12 @@ class lsk_gemm_plan(C.Structure):
                 ("n_tiles", C.c_int32), ("smem_bytes", C.c_int64), ("smem_limit", C.c_int64)]
 
 
+class lsk_attn_plan(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("n_splits", C.c_int32), ("ring_stages", C.c_int32), ("grid", C.c_int32),
+                ("block", C.c_int32), ("row_blocks", C.c_int32), ("kv_refetched_per_row_block", C.c_int32),
+                ("smem_bytes", C.c_int64), ("smem_limit", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/lsk.h declares
 SIGNATURES = {
     "lsk_abi_version": (C.c_int, []),
@@ -102,6 +108,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_float)]),
     "lsk_plan_gemm": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.POINTER(lsk_gemm_plan)]),
+    "lsk_plan_attention": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.POINTER(lsk_attn_plan)]),
     "lsk_test_pack": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "lsk_test_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),

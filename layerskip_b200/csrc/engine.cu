@@ -393,6 +393,31 @@ static int emit_gemm_push_resid(lsk_engine* e, const GemmPlan& p, GemmArgs a, fl
   return LSK_OK;
 }
 
+// Host-side launch plan of the attention kernel (pure host logic; lsk_plan_attention exposes it):
+// split count = engine constant (batch invariance), ring depth as deep as shared memory allows, and a
+// shared-memory floor that gives a one-wave grid a whole SM per CTA (profiles/r2_attention_sweep.md).
+static int attn_default_splits(int sm_count, int kv_heads_local) {
+  return std::max(1, std::min(4, sm_count / std::max(1, kv_heads_local)));
+}
+struct AttnLaunchPlan {
+  AttnSmemPlan sp;
+  int stages;
+  size_t smem;
+  bool ok;
+};
+static AttnLaunchPlan plan_attention_launch(int head_dim, int group, int M, int kv_heads_local, int n_splits,
+                                            int want_stages, int sm_count) {
+  AttnLaunchPlan p;
+  int st = want_stages;
+  while (st > 2 && attn_smem_plan(head_dim, group, M, st).total > (size_t)kSmemMax) --st;
+  p.sp = attn_smem_plan(head_dim, group, M, st);
+  p.stages = st;
+  p.ok = p.sp.total <= (size_t)kSmemMax;
+  p.smem = p.sp.total;
+  if (kv_heads_local * n_splits <= sm_count && p.smem < (size_t)116 * 1024) p.smem = (size_t)116 * 1024;
+  return p;
+}
+
 // Attention over the paged cache: the splits of one kv head = one thread-block cluster (DSMEM
 // merge); head_dim selects the instantiation, the shared-memory plan depends on (group, M).
 template <int HD>
@@ -406,11 +431,10 @@ static int launch_attention_t(lsk_engine* e, AttnArgs& a) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured.fetch_or(bit, std::memory_order_relaxed);
   }
-  int st = e->attn_stages;
-  while (st > 2 && attn_smem_plan(HD, a.group, a.M, st).total > (size_t)kSmemMax) --st;
-  const AttnSmemPlan sp = attn_smem_plan(HD, a.group, a.M, st);
-  a.n_stages = st;
-  if (sp.total > (size_t)kSmemMax)
+  const AttnLaunchPlan lp = plan_attention_launch(HD, a.group, a.M, a.n_kv_heads, a.n_splits, e->attn_stages, e->sm_count);
+  const AttnSmemPlan& sp = lp.sp;
+  a.n_stages = lp.stages;
+  if (!lp.ok)
     return fail(LSK_ERR_INVALID, "attention: %d query rows per kv head do not fit shared memory", a.group * a.M);
   a.rows_pad = (a.group * a.M + 15) / 16 * 16;
   a.merge_off = sp.merge_off; a.part_off = sp.part_off; a.reload_per_rb = sp.reload_per_rb;
@@ -419,9 +443,7 @@ static int launch_attention_t(lsk_engine* e, AttnArgs& a) {
   cfg.blockDim = dim3(kAttnThreads);
   // a grid that fits one wave gets a whole SM per CTA (> half of the SM's shared memory): the
   // CTAs then spread over the SMs instead of sharing a few SMs' load bandwidth
-  size_t smem = sp.total;
-  if (a.n_kv_heads * a.n_splits <= e->sm_count && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = lp.smem;
   cfg.stream = e->stream;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -956,7 +978,7 @@ static int create_into(lsk_engine* e, const lsk_config& c) {
   // bandwidth and barrier latency, so the best grid is ONE CTA per SM on as many SMs as possible —
   // splits = floor(SMs / kv heads), at most 4 (7B: 32 heads x 4 splits; an 8-CTA cluster's barrier
   // and 8-way merge cost more than the extra SMs bring: 16 heads x 8 splits ran 23 us against 15).
-  e->n_splits = c.attn_splits > 0 ? c.attn_splits : std::max(1, std::min(4, e->sm_count / std::max(1, e->kv_heads_l)));
+  e->n_splits = c.attn_splits > 0 ? c.attn_splits : attn_default_splits(e->sm_count, e->kv_heads_l);
   if (const char* env = getenv("LSK_ATTN_SPLITS")) e->n_splits = atoi(env);   // clamped to [1, 8] below
   if (const char* env = getenv("LSK_ATTN_STAGES")) e->attn_stages = atoi(env);
   if (e->attn_stages < 2) e->attn_stages = 2;
@@ -1659,6 +1681,27 @@ int lsk_plan_gemm(int64_t n_rows, int64_t K, int32_t m, int32_t pro, int32_t epi
   out->smem_bytes = (int64_t)sc.smem;
   out->smem_limit = kSmemMax;
   out->n_tiles = p.n_tiles;
+  return LSK_OK;
+}
+
+// Host-side launch plan of the attention kernel for `m` query rows (no GPU needed).
+int lsk_plan_attention(int32_t head_dim, int32_t n_heads, int32_t n_kv_heads_local, int32_t m, int32_t sm_count,
+                       lsk_attn_plan* out) {
+  if (!out || (head_dim != 32 && head_dim != 64 && head_dim != 128) || n_heads < 1 || n_kv_heads_local < 1 ||
+      n_heads % n_kv_heads_local || m < 1 || sm_count < 1)
+    return fail(LSK_ERR_INVALID, "bad attention plan query");
+  const int group = n_heads / n_kv_heads_local;
+  const int splits = attn_default_splits(sm_count, n_kv_heads_local);
+  const AttnLaunchPlan p = plan_attention_launch(head_dim, group, m, n_kv_heads_local, splits, kAttnMaxStages, sm_count);
+  out->ok = p.ok ? 1 : 0;
+  out->n_splits = splits;
+  out->ring_stages = p.stages;
+  out->grid = n_kv_heads_local * splits;
+  out->block = kAttnThreads;
+  out->row_blocks = (group * m + 15) / 16;
+  out->kv_refetched_per_row_block = p.sp.reload_per_rb;
+  out->smem_bytes = (int64_t)p.smem;
+  out->smem_limit = kSmemMax;
   return LSK_OK;
 }
 

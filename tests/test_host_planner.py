@@ -74,3 +74,35 @@ def test_bad_queries_are_rejected():
     assert lib.lsk_plan_gemm(128, 100, 1, 0, 0, SMS, C.byref(out)) != 0       # k % 32
     assert lib.lsk_plan_gemm(128, 4096, 17, 0, 0, SMS, C.byref(out)) != 0     # rows > 16
     assert b"bad plan query" in lib.lsk_last_error()
+
+
+def attn_plan(arch, m, tp=1, sms=SMS):
+    lib = _lib.load()
+    out = _lib.lsk_attn_plan()
+    _lib.check(lib.lsk_plan_attention(arch.head_dim, arch.heads // tp, arch.kv_heads // tp, m, sms, C.byref(out)))
+    return out
+
+
+def test_attention_launch_plan_for_the_baseline_architectures():
+    """engine.cu: attn_default_splits / plan_attention_launch (through lsk_plan_attention): the split
+    count is min(4, SMs / local kv heads), the K/V ring is as deep as shared memory allows, and a grid
+    that fits one wave gets more than half an SM's shared memory per CTA (one CTA per SM)."""
+    p = attn_plan(ARCHS["llama2-7b"], 7)                       # 32 kv heads: 32 x 4 CTAs on 148 SMs
+    assert (p.ok, p.n_splits, p.grid, p.ring_stages, p.row_blocks) == (1, 4, 128, 4, 1)
+    assert p.smem_bytes > 114 * 1024 and p.kv_refetched_per_row_block == 1   # merge buffer aliases the ring
+    p = attn_plan(ARCHS["llama3-8b"], 7)                       # GQA 4: 28 query rows -> 2 row blocks, K/V resident
+    assert (p.n_splits, p.grid, p.row_blocks, p.kv_refetched_per_row_block) == (4, 32, 2, 0)
+    p = attn_plan(ARCHS["llama2-13b"], 7)                      # 40 kv heads -> 3 splits (120 CTAs)
+    assert (p.n_splits, p.grid) == (3, 120)
+    p = attn_plan(ARCHS["llama2-70b"], 7, tp=8)                # one kv head per rank, 8 q heads share it
+    assert (p.ok, p.n_splits, p.grid, p.row_blocks) == (1, 4, 4, 4)
+    p = attn_plan(ARCHS["llama2-7b"], 128)                     # prompt pass: 128 query rows per launch
+    assert p.ok == 1 and p.row_blocks == 8 and p.smem_bytes <= p.smem_limit
+    p = attn_plan(ARCHS["llama3-8b"], 128)                     # 512 rows do not fit: the engine launches 48 at a time
+    assert p.ok == 0
+    assert attn_plan(ARCHS["llama3-8b"], 48).ok == 1
+    p = attn_plan(ARCHS["llama3.2-1b"], 16)                    # head_dim 64: 8 KiB K/V blocks
+    assert p.ok == 1 and p.ring_stages == 4
+    for bad in ((96, 32, 32, 7), (128, 32, 5, 7), (128, 32, 32, 0)):
+        out = _lib.lsk_attn_plan()
+        assert _lib.load().lsk_plan_attention(bad[0], bad[1], bad[2], bad[3], SMS, C.byref(out)) == -1

@@ -243,7 +243,9 @@ static GemmSched plan_sched(int NT, int M, int pro, int epi, const GemmPlan& p, 
   constexpr int fixed_ring = 0;
   GemmSched best;
   for (int want = 1; want <= 16; ++want) {
-    if (pro == PRO_RMS && want > 1) break;          // RMSNorm needs the whole row resident
+    // RMSNorm prologue: whole rows resident whenever that fits; otherwise (16-row blocks at hidden
+    // > 4096) the statistics are computed up front and the rows are normalised chunk by chunk
+    if (pro == PRO_RMS && want == 2 && best.ok) break;   // whole rows fit: keep the resident mode
     int kc = (p.nsb + want - 1) / want;
     if (want > 1) kc = (kc + kStageSbs - 1) / kStageSbs * kStageSbs;
     const int n_chunks = (p.nsb + kc - 1) / kc;

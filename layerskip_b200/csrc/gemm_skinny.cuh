@@ -215,6 +215,43 @@ __device__ __forceinline__ void gemm_load_x_bf16(const GemmArgs& a, unsigned cha
   }
 }
 
+// K-chunked RMSNorm mode: chunk kc of the fp32 residual rows -> normalised bf16 activation chunk,
+// with the rstd the prologue left in `rstd[m]`; same rounding as the resident mode
+// (bf16(w * (x * rstd)), modeling_llama.py:52-70).  Four rows per step, loads issued together.
+template <int NT>
+__device__ __forceinline__ void gemm_load_x_rms(const GemmArgs& a, unsigned char* xs, int XS, int kc_cols,
+                                                int kc, const float* rstd, int ltid, int nthreads) {
+  const int col0 = kc * kc_cols;
+  const int cols = min(a.K - col0, kc_cols);
+  const int nvec = cols >> 2;                // float4 per row in this chunk
+  const int zvec = kc_cols >> 2;
+  for (int m0 = 0; m0 < a.xs_rows; m0 += 4) {
+    for (int idx = ltid; idx < zvec; idx += nthreads) {
+      float4 v[4];
+      uint2 wv = make_uint2(0, 0);
+      if (idx < nvec) wv = *reinterpret_cast<const uint2*>(a.norm_w + col0 + idx * 4);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < a.M && idx < nvec)
+          v[r] = *reinterpret_cast<const float4*>(a.x_f32 + (size_t)(m0 + r) * a.x_ld + col0 + idx * 4);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = m0 + r;
+        if (m >= a.xs_rows) continue;
+        uint2 o = make_uint2(0u, 0u);
+        if (m < a.M && idx < nvec) {
+          const float rs = rstd[m];
+          o.x = pack_bf16x2(bf16_lo(wv.x) * (v[r].x * rs), bf16_hi(wv.x) * (v[r].y * rs));
+          o.y = pack_bf16x2(bf16_lo(wv.y) * (v[r].z * rs), bf16_hi(wv.y) * (v[r].w * rs));
+        }
+        *reinterpret_cast<uint2*>(xs + (size_t)m * XS + idx * 8) = o;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PROLOGUE (consumer + epilogue warps, kWorkThreads): activations -> bf16 rows in scratch.
 // Ends with a BAR_WORK sync.
@@ -233,7 +270,7 @@ __device__ __forceinline__ void gemm_preload_norm(const GemmArgs& a, int wtid, u
 // ROWS residual rows at a time: each thread pulls its VEC float4 slices of all ROWS rows into
 // registers at once, the group's sums of squares are reduced across the work threads (2 barriers),
 // and the rows are normalised out of registers into the activation block.
-template <int NT, int ROWS, int VEC>
+template <int NT, int ROWS, int VEC, bool STATS_ONLY = false>
 __device__ __forceinline__ void rms_rows_group(const GemmArgs& a, unsigned char* xs, int XS, int kc_cols,
                                                float* stat, int wtid, int swarp, int lane,
                                                const uint2 (&wreg)[4]) {
@@ -268,6 +305,7 @@ __device__ __forceinline__ void rms_rows_group(const GemmArgs& a, unsigned char*
       stat[kStatWarps * NT * 8 + m0 + wtid] = rsqrtf(tot / (float)a.K + a.eps);
     }
     bar_sync(BAR_WORK, kWorkThreads);
+    if (STATS_ONLY) continue;                  // K-chunked mode: rows are normalised per chunk later
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int m = m0 + r;
@@ -312,7 +350,13 @@ __device__ __forceinline__ void gemm_prologue(const GemmArgs& a, const GemmCtx& 
     // K <= 4864: 2 slices per thread and row -> groups of 4 rows; larger K: 4 slices -> groups of 2.
     // (Groups of 8 rows were measured: the 64 live registers spill inside the 96-register budget of
     // the 640-thread CTA and the round got 9 % SLOWER, 7.32 vs 6.70 ms.)
-    if ((a.K >> 2) <= 2 * kWorkThreads) rms_rows_group<NT, 4, 2>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
+    // K-chunked (n_chunks > 1: 16-row blocks at hidden > 4096): only the statistics here — the SAME
+    // reduction as the resident mode, so a row's rstd does not depend on how the block is staged —
+    // and gemm_load_x_rms normalises each chunk when the consumers swap it in.
+    if (a.n_chunks > 1) {
+      if ((a.K >> 2) <= 2 * kWorkThreads) rms_rows_group<NT, 4, 2, true>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
+      else rms_rows_group<NT, 2, 4, true>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
+    } else if ((a.K >> 2) <= 2 * kWorkThreads) rms_rows_group<NT, 4, 2>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
     else rms_rows_group<NT, 2, 4>(a, xs, XS, kc_cols, stat, wtid, swarp, lane, wreg);
   } else if (a.n_chunks == 1) {
     gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, 0, wtid, kWorkThreads);
@@ -353,7 +397,12 @@ __device__ __forceinline__ void gemm_consume(const GemmArgs& a, const GemmCtx& c
     for (int kc = 0; kc < a.n_chunks; ++kc) {
       if (a.n_chunks > 1) {            // swap the resident activation chunk
         bar_sync(BAR_CONS, kConsumerThreads);
-        gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, kc, tid, kConsumerThreads);
+        if (a.x_f32 != nullptr && a.norm_w != nullptr) {   // PRO_RMS, K-chunked
+          const float* rstd = reinterpret_cast<const float*>(c.scratch + L.stat) + (kGemmWarps + kEpiWarps) * NT * 8;
+          gemm_load_x_rms<NT>(a, xs, XS, kc_cols, kc, rstd, tid, kConsumerThreads);
+        } else {
+          gemm_load_x_bf16<NT>(a, xs, XS, kc_cols, kc, tid, kConsumerThreads);
+        }
         bar_sync(BAR_CONS, kConsumerThreads);
       }
       const int sb_lo = kc * a.kc_sbs;

@@ -62,9 +62,16 @@ def test_sixteen_row_blocks_and_their_limits():
     n, k, pro, epi = gemms_of(a)["qkv"]
     p = plan(n, k, 16, pro, epi)
     assert p.ok and p.nt == 2
-    n, k, pro, epi = gemms_of(ARCHS["llama2-70b"], 8)["qkv"]      # hidden 8192: RMS rows stay whole
-    assert not plan(n, k, 16, pro, epi).ok
-    assert plan(n, k, 8, pro, epi).ok
+    assert p.n_chunks == 1                                        # hidden 4096: 16 whole rows fit
+    # hidden 8192 / 5120: 16 whole rows do not fit next to the ring -> K-chunked RMSNorm mode
+    # (statistics up front, rows normalised chunk by chunk); up to 8 rows stay resident as before
+    for name, tp in (("llama2-70b", 8), ("llama2-13b", 1)):
+        for key in ("qkv", "gate_up", "lm_head"):
+            n, k, pro, epi = gemms_of(ARCHS[name], tp)[key]
+            p16, p8 = plan(n, k, 16, pro, epi), plan(n, k, 8, pro, epi)
+            assert p16.ok and p16.nt == 2 and p16.n_chunks > 1 and p16.tiles_per_pass == 2, (name, key)
+            assert p16.ring_stages >= 2 and p16.smem_bytes <= p16.smem_limit
+            assert p8.ok and p8.n_chunks == 1, (name, key)
 
 
 def test_bad_queries_are_rejected():

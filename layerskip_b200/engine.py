@@ -70,13 +70,6 @@ class Engine:
             rope_original_max_pos=arch.rope_original_max_pos)
         self.max_ctx = max_ctx
         self.keep_logits = keep_logits
-        # token rows one step can carry (engine.cu: max_rows): 16 when the host planner finds a
-        # schedule for the 16-row RMSNorm GEMM at K = hidden (whole rows resident up to hidden 4096,
-        # K-chunked normalisation above), else 8
-        plan = _lib.lsk_gemm_plan()
-        qkv_rows = (arch.heads + 2 * arch.kv_heads) // tp_size * arch.head_dim
-        ok = self._lib.lsk_plan_gemm((qkv_rows + 15) // 16 * 16, arch.hidden, 16, 0, 0, 148, C.byref(plan))
-        self.max_rows = 16 if (ok == 0 and plan.ok) else 8
         # refuse a configuration that cannot fit BEFORE cudaMalloc fails half-way (memory.py)
         try:
             free_bytes = torch.cuda.mem_get_info(self.device)[0]
@@ -92,6 +85,13 @@ class Engine:
             _lib.check(self._lib.lsk_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
         self._exit_layer = -1
+        # token rows one step can carry (engine.cu: max_rows): 16 when the host planner finds a
+        # schedule for the 16-row RMSNorm GEMM at K = hidden (whole rows resident up to hidden 4096,
+        # K-chunked normalisation above), else 8
+        plan = _lib.lsk_gemm_plan()
+        qkv_rows = (arch.heads + 2 * arch.kv_heads) // tp_size * arch.head_dim
+        ok = self._lib.lsk_plan_gemm((qkv_rows + 15) // 16 * 16, arch.hidden, 16, 0, 0, 148, C.byref(plan))
+        self.max_rows = 16 if (ok == 0 and plan.ok) else 8
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:

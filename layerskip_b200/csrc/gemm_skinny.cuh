@@ -114,8 +114,7 @@ __host__ __device__ inline int gemm_x_stride_bytes(int kcols) {
 
 // shared-memory carve-up (host and device must agree).  Fixed part: mbarriers + ring; the
 // SCRATCH region behind it holds, per GEMM, the activation block, the partial-tile slots, RMS
-// statistics and the LM-head logits tile (and is reused by the attention teams of the step
-// megakernel).
+// statistics and the LM-head logits tile.
 constexpr int kBarBytes = 1024;
 struct GemmScratch {
   size_t xs, red, stat, lg, total;
@@ -162,7 +161,7 @@ __device__ __forceinline__ void ctx_init_barriers(const GemmCtx& c) {   // one t
 // ---------------------------------------------------------------------------------------------
 // PRODUCER (one lane): walk this CTA's weight byte stream, tile after tile in 16 KiB stages, and
 // issue TMA bulk copies into the ring as slots free up.  `q` counts stages over the kernel's
-// lifetime (it continues across the GEMM stages of the step megakernel).
+// lifetime.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_producer(const GemmArgs& a, const GemmCtx& c, uint32_t& q) {
   const int TPP = a.tiles_per_pass;

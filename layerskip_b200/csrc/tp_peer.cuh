@@ -1,6 +1,9 @@
 // tp_peer.cuh — one-shot collectives over peer-mapped HBM (NVLink 5 / NVSwitch) for the
-// tensor-parallel engine.  OPT-IN (LSK_FLAG_TP_ONESHOT / LSK_TP_ONESHOT=1); the default TP path
-// uses NCCL (engine.cu: enqueue_layer).
+// tensor-parallel engine.  This is the DEFAULT data path under tensor parallelism
+// (LSK_TP_ONESHOT selects the protocol, 0 = NCCL; engine.cu: emit_allreduce_resid /
+// emit_gemm_push_resid); the measured comparison is profiles/r2_tp2_modes.md.  The fence + flag
+// protocol described first is round 1's design (mode 3); the LL protocol further down (modes 1 and
+// 2, the default) replaced it after it measured 24 % slower.
 //
 // Why: a round of the TP engine performs 2 x [(d+1) E + (L-E)] all-reduces of <= 16 x hidden fp32
 // (176 per round at 13B) plus d+1 arg-max exchanges, every one on the critical
